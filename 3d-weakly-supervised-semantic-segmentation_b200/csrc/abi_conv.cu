@@ -1,0 +1,56 @@
+// abi_conv.cu -- C-ABI dispatch for the convolution entry points (fp32 CUDA-core vs TF32 tcgen05 paths).
+#include "common.cuh"
+
+namespace b200scn {
+int gather_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *W,
+                     int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
+                     cudaStream_t st);
+int scatter_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K, const float *W,
+                      int Cin, int Cout, float *out, int64_t ldo, cudaStream_t st);
+int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                 const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
+                 float *dW, cudaStream_t st);
+}  // namespace b200scn
+
+using namespace b200scn;
+
+extern "C" {
+
+int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K,
+                        const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
+                        float *out, int64_t ldo, int precision, void *stream) {
+  if (n_out <= 0) return 0;
+  if (!map && K != 1) return set_error("gather_conv: identity map requires K == 1");
+  if (K < 1 || K > 64) return set_error("gather_conv: K=%d outside [1,64]", K);
+  if (Cin < 1 || Cout < 1) return set_error("gather_conv: bad channel counts %d -> %d", Cin, Cout);
+  if (n_out >= ((int64_t)1 << 31)) return set_error("gather_conv: too many rows");
+  (void)precision;
+  return gather_conv_simt(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+}
+
+int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,
+                         const float *W, int Cin, int Cout, float *out, int64_t ldo, int precision,
+                         void *stream) {
+  if (n_in <= 0) return 0;
+  if (!map) return set_error("scatter_conv: map is required");
+  if (K < 1 || K > 64) return set_error("scatter_conv: K=%d outside [1,64]", K);
+  if (Cin < 1 || Cout < 1) return set_error("scatter_conv: bad channel counts %d -> %d", Cin, Cout);
+  (void)precision;
+  return scatter_conv_simt(A, lda, map, n_in, K, W, Cin, Cout, out, ldo, (cudaStream_t)stream);
+}
+
+int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                    const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max,
+                    int Ca, int Cg, float *dW, int precision, void *stream) {
+  if (K < 1 || K > 64) return set_error("pair_dw: K=%d outside [1,64]", K);
+  if (!offsets_dev && K != 1) return set_error("pair_dw: a single list requires K == 1");
+  (void)precision;
+  return pair_dw_simt(A, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, Ca, Cg, dW, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+extern "C" int b200scn_set_device(int device) {
+  SCN_CUDA(cudaSetDevice(device));
+  return 0;
+}

@@ -1,0 +1,270 @@
+// bn.cu -- BatchNormReLU / BatchNormLeakyReLU over the active rows.
+//
+// Replaces upstream scn's BatchNormalization_f_train kernel, whose grid is nPlanes/32 blocks (ONE block
+// at m=32).  Here the per-channel reductions run over a full grid (4 CTAs per SM), each CTA reducing a
+// contiguous slab of rows with 16-byte loads, fp32 thread partials, double accumulation across CTAs.
+// Pure HBM-bound: forward = read x twice + write y, backward = read x,dy twice + write dx.
+#include "common.cuh"
+
+namespace b200scn {
+
+__device__ __forceinline__ float bn_affine(float x, float mean, float invstd, float w, float b) {
+  return fmaf((x - mean) * invstd, w, b);
+}
+
+struct BnCfg {
+  int tpr;   // threads per row (each thread owns VEC consecutive channels)
+  int rps;   // rows per block step
+};
+static inline BnCfg bn_cfg(int C, int vec) {
+  BnCfg c;
+  c.tpr = (int)ceil_div(C, vec);
+  c.rps = 256 / c.tpr;
+  if (c.rps < 1) c.rps = 1;
+  return c;
+}
+
+// MODE 0: sums of x and x^2.   MODE 1: sums of g and (x-mean)*g with g = dy * relu'(y).
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(256)
+bn_reduce_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ dy, int64_t lddy,
+                 int64_t n, int C, int tpr, int rps, int64_t rows_per_block,
+                 const float *__restrict__ mean, const float *__restrict__ invstd,
+                 const float *__restrict__ weight, const float *__restrict__ bias, float leak,
+                 double *__restrict__ sums /*2*C*/) {
+  extern __shared__ float red[];  // rps * C * 2
+  const int tid = threadIdx.x;
+  const int rg = tid / tpr, ct = tid - rg * tpr;
+  const int c0 = ct * VEC;
+  const bool active = rg < rps && c0 < C;
+  float s0[VEC], s1[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) s0[v] = s1[v] = 0.f;
+  float m[VEC], is[VEC], w[VEC], b[VEC];
+  if (MODE == 1 && active) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      m[v] = mean[c0 + v]; is[v] = invstd[c0 + v]; w[v] = weight[c0 + v]; b[v] = bias[c0 + v];
+    }
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, n);
+  if (active) {
+    for (int64_t r = r0 + rg; r < r1; r += rps) {
+      float xv[VEC], gv[VEC];
+      if (VEC == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
+        xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        if (MODE == 1) {
+          float4 u = __ldg(reinterpret_cast<const float4 *>(dy + r * lddy + c0));
+          gv[0] = u.x; gv[1] = u.y; gv[2] = u.z; gv[3] = u.w;
+        }
+      } else {
+        xv[0] = __ldg(x + r * ldx + c0);
+        if (MODE == 1) gv[0] = __ldg(dy + r * lddy + c0);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (MODE == 0) {
+          s0[v] += xv[v];
+          s1[v] = fmaf(xv[v], xv[v], s1[v]);
+        } else {
+          float y = bn_affine(xv[v], m[v], is[v], w[v], b[v]);
+          float g = y > 0.f ? gv[v] : leak * gv[v];
+          s0[v] += g;
+          s1[v] = fmaf(xv[v] - m[v], g, s1[v]);
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      red[(rg * C + c0 + v) * 2 + 0] = s0[v];
+      red[(rg * C + c0 + v) * 2 + 1] = s1[v];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < 2 * C; e += 256) {
+    int c = e >> 1, which = e & 1;
+    double acc = 0.0;
+    for (int g = 0; g < rps; ++g) acc += (double)red[(g * C + c) * 2 + which];
+    atomicAdd(sums + which * C + c, acc);
+  }
+}
+
+__global__ void bn_finalize_fwd_kernel(const double *__restrict__ sums, int64_t n, int C,
+                                       float *running_mean, float *running_var, float momentum,
+                                       float eps, float *save_mean, float *save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sums[c] / (double)n;
+  double var = sums[C + c] / (double)n - mean * mean;
+  if (var < 0) var = 0;
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+  running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+  running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)unbiased;
+}
+
+__global__ void bn_eval_stats_kernel(int C, const float *running_mean, const float *running_var,
+                                     float eps, float *save_mean, float *save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  save_mean[c] = running_mean[c];
+  save_invstd[c] = rsqrtf(running_var[c] + eps);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float *__restrict__ x, int64_t ldx, int64_t n, int C, const float *__restrict__ mean,
+                const float *__restrict__ invstd, const float *__restrict__ weight,
+                const float *__restrict__ bias, float leak, float *__restrict__ y, int64_t ldy) {
+  const int cv = C / VEC;
+  const int64_t total = n * cv;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / cv;
+    int c0 = (int)(t - r * cv) * VEC;
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
+      float4 mm = __ldg(reinterpret_cast<const float4 *>(mean + c0));
+      float4 ii = __ldg(reinterpret_cast<const float4 *>(invstd + c0));
+      float4 ww = __ldg(reinterpret_cast<const float4 *>(weight + c0));
+      float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + c0));
+      float4 o;
+      o.x = bn_affine(v.x, mm.x, ii.x, ww.x, bb.x); o.x = o.x > 0.f ? o.x : leak * o.x;
+      o.y = bn_affine(v.y, mm.y, ii.y, ww.y, bb.y); o.y = o.y > 0.f ? o.y : leak * o.y;
+      o.z = bn_affine(v.z, mm.z, ii.z, ww.z, bb.z); o.z = o.z > 0.f ? o.z : leak * o.z;
+      o.w = bn_affine(v.w, mm.w, ii.w, ww.w, bb.w); o.w = o.w > 0.f ? o.w : leak * o.w;
+      *reinterpret_cast<float4 *>(y + r * ldy + c0) = o;
+    } else {
+      float o = bn_affine(__ldg(x + r * ldx + c0), mean[c0], invstd[c0], weight[c0], bias[c0]);
+      y[r * ldy + c0] = o > 0.f ? o : leak * o;
+    }
+  }
+}
+
+__global__ void bn_finalize_bwd_kernel(const double *__restrict__ sums, int C,
+                                       const float *__restrict__ invstd, float *d_weight, float *d_bias) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  d_bias[c] = (float)sums[c];
+  d_weight[c] = (float)(sums[C + c] * (double)invstd[c]);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ dy, int64_t lddy,
+                    int64_t n, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
+                    const float *__restrict__ weight, const float *__restrict__ bias, float leak,
+                    const double *__restrict__ sums, float *__restrict__ dx, int64_t lddx) {
+  const int cv = C / VEC;
+  const int64_t total = n * cv;
+  const float inv_n = 1.f / (float)n;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t / cv;
+    int c0 = (int)(t - r * cv) * VEC;
+    float xv[VEC], gv[VEC], ov[VEC];
+    if (VEC == 4) {
+      float4 a = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
+      float4 g = __ldg(reinterpret_cast<const float4 *>(dy + r * lddy + c0));
+      xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+      gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+    } else {
+      xv[0] = __ldg(x + r * ldx + c0);
+      gv[0] = __ldg(dy + r * lddy + c0);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      int c = c0 + v;
+      float m = __ldg(mean + c), is = __ldg(invstd + c), w = __ldg(weight + c), b = __ldg(bias + c);
+      float yv = bn_affine(xv[v], m, is, w, b);
+      float g = yv > 0.f ? gv[v] : leak * gv[v];
+      float sg = (float)sums[c], dot = (float)sums[C + c];
+      ov[v] = (g - sg * inv_n - (xv[v] - m) * dot * is * is * inv_n) * is * w;
+    }
+    if (VEC == 4) *reinterpret_cast<float4 *>(dx + r * lddx + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    else dx[r * lddx + c0] = ov[0];
+  }
+}
+
+static bool vec_ok(int C, int64_t ld, const void *p) {
+  return C % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+template <int MODE>
+static int launch_reduce(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
+                         const float *mean, const float *invstd, const float *weight, const float *bias,
+                         float leak, double *sums, bool vec, cudaStream_t st) {
+  BnCfg cfg = bn_cfg(C, vec ? 4 : 1);
+  if (cfg.tpr > 256) return set_error("batchnorm: %d planes unsupported on this path", C);
+  int64_t blocks = kNumSMs * 4;
+  int64_t rows_per_block = ceil_div(n, blocks);
+  if (rows_per_block < cfg.rps) rows_per_block = cfg.rps;
+  blocks = ceil_div(n, rows_per_block);
+  size_t smem = sizeof(float) * 2 * (size_t)cfg.rps * C;
+  if (smem > 48 * 1024) return set_error("batchnorm: shared memory %zu too large", smem);
+  if (vec)
+    bn_reduce_kernel<4, MODE><<<(unsigned)blocks, 256, smem, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, mean, invstd, weight, bias, leak, sums);
+  else
+    bn_reduce_kernel<1, MODE><<<(unsigned)blocks, 256, smem, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, mean, invstd, weight, bias, leak, sums);
+  SCN_CHECK_LAUNCH("bn_reduce");
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace b200scn
+
+using namespace b200scn;
+
+extern "C" {
+
+int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const float *weight,
+                       const float *bias, float *running_mean, float *running_var, float *save_mean,
+                       float *save_invstd, float eps, float momentum, int train, float leak, float *y,
+                       int64_t ldy, double *scratch, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 0) return set_error("batchnorm: C must be positive");
+  const bool vec = vec_ok(C, ldx, x) && vec_ok(C, ldy, y) && vec_ok(C, 4, weight) && vec_ok(C, 4, bias) &&
+                   vec_ok(C, 4, save_mean) && vec_ok(C, 4, save_invstd);
+  const unsigned cb = (unsigned)ceil_div(C, 128);
+  if (train && n > 0) {
+    SCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+    if (launch_reduce<0>(x, ldx, nullptr, 0, n, C, nullptr, nullptr, nullptr, nullptr, 0.f, scratch, vec, st)) return 1;
+    bn_finalize_fwd_kernel<<<cb, 128, 0, st>>>(scratch, n, C, running_mean, running_var, momentum, eps, save_mean, save_invstd);
+  } else {
+    bn_eval_stats_kernel<<<cb, 128, 0, st>>>(C, running_mean, running_var, eps, save_mean, save_invstd);
+  }
+  if (n > 0) {
+    int64_t total = n * (vec ? C / 4 : C);
+    unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(total, 256));
+    if (vec) bn_apply_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, n, C, save_mean, save_invstd, weight, bias, leak, y, ldy);
+    else bn_apply_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, n, C, save_mean, save_invstd, weight, bias, leak, y, ldy);
+  }
+  SCN_CHECK_LAUNCH("bn_forward");
+  count_launch(n > 0 ? 2 : 1);
+  return 0;
+}
+
+int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
+                        const float *weight, const float *bias, const float *save_mean,
+                        const float *save_invstd, float leak, float *dx, int64_t lddx, float *d_weight,
+                        float *d_bias, double *scratch, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = vec_ok(C, ldx, x) && vec_ok(C, lddy, dy) && vec_ok(C, lddx, dx);
+  SCN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * C, st));
+  if (n > 0 && launch_reduce<1>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, vec, st)) return 1;
+  bn_finalize_bwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(scratch, C, save_invstd, d_weight, d_bias);
+  if (n > 0) {
+    int64_t total = n * (vec ? C / 4 : C);
+    unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(total, 256));
+    if (vec) bn_bwd_apply_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
+    else bn_bwd_apply_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
+  }
+  SCN_CHECK_LAUNCH("bn_backward");
+  count_launch(n > 0 ? 2 : 1);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+"""sparseconvnet -- B200-native drop-in for the `sparseconvnet` ("scn") operator layer used by
+timsu1104/3D-Weakly-Supervised-Semantic-Segmentation (`import sparseconvnet as scn`,
+models/SparseConvNet.py:5).  Same module names and call signatures; every sparse op runs as a
+hand-written sm_100a CUDA kernel behind the C ABI in include/b200scn.h.  No CPU fallback, no Triton.
+"""
+import sys
+import types
+
+from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
+from ._lib import B200SCNError, launch_count
+from .metadata import Metadata, set_pyramid_hint
+from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, ConcatTable, Convolution,
+                      Deconvolution, Identity, InputLayer, JoinTable, NetworkInNetwork, OutputLayer, Sequential,
+                      SparseConvNetTensor, SubmanifoldConvolution, UnPooling)
+from .networks import FullyConvolutionalNet, UNet
+from .ops import get_precision, set_precision
+from .utils import checkpoint_restore, checkpoint_save, is_power2
+
+forward_pass_hidden_states = 0
+
+
+class _Module(types.ModuleType):
+    """Module subclass so `scn.forward_pass_multiplyAdd_count` (train.py:50,86) stays a plain number for the
+    caller while rule counts are resolved lazily (they live on the device until somebody looks)."""
+
+    @property
+    def forward_pass_multiplyAdd_count(self):
+        total = self.__dict__["_madd_base"]
+        for src, mult in self.__dict__["_madd_pending"]:
+            n = sum(src.rule_counts()) if hasattr(src, "rule_counts") else int(src)
+            total += n * mult
+        self.__dict__["_madd_base"] = total
+        self.__dict__["_madd_pending"] = []
+        return total
+
+    @forward_pass_multiplyAdd_count.setter
+    def forward_pass_multiplyAdd_count(self, value):
+        self.__dict__["_madd_base"] = value
+        self.__dict__["_madd_pending"] = []
+
+    def _add_madds(self, src, mult):
+        pend = self.__dict__["_madd_pending"]
+        pend.append((src, mult))
+        if len(pend) > 4096:  # nobody is reading the counter: fold what is already known
+            _ = self.forward_pass_multiplyAdd_count
+
+
+_self = sys.modules[__name__]
+_self.__dict__["_madd_base"] = 0
+_self.__dict__["_madd_pending"] = []
+_self.__class__ = _Module

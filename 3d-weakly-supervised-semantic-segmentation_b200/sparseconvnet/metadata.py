@@ -1,0 +1,221 @@
+"""Device-resident Metadata: active-site grids and rulebooks for one forward/backward.
+
+Mirrors the role of upstream scn's `Metadata_3`: one object per InputLayer call,
+shared by reference by every SparseConvNetTensor derived from it, owning every grid / rulebook.
+Unlike upstream (CPU hash maps, rules copied H2D on every conv call) everything lives in HBM and
+the host synchronises exactly once per forward (to learn the per-level site counts).
+"""
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+# speculative pyramid built inside InputLayer before its single host sync: (stride, coarse levels)
+_pyramid_hint = [2, 6]
+
+
+def set_pyramid_hint(stride, depth):
+    """Stride and number of coarse levels pre-built per forward (default 2, 6 = the 7-level UNet/FCNet).
+    Nets with another stride (e.g. downsample=[4,4]) still work: their pyramid is built on demand with
+    one extra host sync."""
+    _pyramid_hint[0], _pyramid_hint[1] = int(stride), int(depth)
+
+
+class Level:
+    """One spatial size: its sites (keys in id order), hash table, lazily built 3^3 neighbour map and pair lists."""
+
+    def __init__(self, size, n, ukeys, hkeys, hvals, cap):
+        self.size, self.n, self.ukeys, self.hkeys, self.hvals, self.cap = size, n, ukeys, hkeys, hvals, cap
+        self.nbr = None           # (n,27) int32
+        self.nbr_counts = None    # (27,) int32 device: rules per offset
+        self.pairs = None         # (pair_in, pair_out, offsets_dev)
+        self._counts = None
+
+    def subm_map(self):
+        if self.nbr is None:
+            dev = self.ukeys.device
+            self.nbr = torch.empty((self.n, 27), dtype=torch.int32, device=dev)
+            self.nbr_counts = torch.zeros(27, dtype=torch.int32, device=dev)
+            st = _lib.stream_for(self.ukeys)
+            check(lib.b200scn_subm_map(ptr(self.ukeys), self.n, None, ptr(self.hkeys), ptr(self.hvals), self.cap,
+                                       self.size, ptr(self.nbr), ptr(self.nbr_counts), st))
+            # rule counts travel to the host asynchronously; nobody waits for them unless the op counters
+            # are read or a weight gradient needs exact pair-list sizes (long after this point)
+            self._counts_host = torch.empty(27, dtype=torch.int32, pin_memory=True)
+            self._counts_host.copy_(self.nbr_counts, non_blocking=True)
+            self._counts_event = torch.cuda.Event()
+            self._counts_event.record(torch.cuda.current_stream(dev))
+        return self.nbr
+
+    def rule_counts(self):
+        """Rules per kernel offset (host ints)."""
+        self.subm_map()
+        if self._counts is None:
+            self._counts_event.synchronize()
+            self._counts = [int(v) for v in self._counts_host]
+        return self._counts
+
+    def subm_pairs(self):
+        if self.pairs is None:
+            self.pairs = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()))
+        return self.pairs
+
+
+def build_pairs(map_t, n, K, total):
+    """scn-form rulebook (per-offset (in,out) pair lists, ascending out) from a map[n][K] with `total` entries >= 0."""
+    dev = map_t.device
+    offsets = torch.empty(K + 1, dtype=torch.int32, device=dev)
+    nbytes = lib.b200scn_pair_scratch_bytes(n, K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    pair_in = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    pair_out = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    st = _lib.stream_for(map_t)
+    check(lib.b200scn_pair_lists(ptr(map_t), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets), ptr(scratch), nbytes, st))
+    return pair_in, pair_out, offsets
+
+
+class Down:
+    """Strided relation fine(size) -> coarse(size//s): parent/off per fine site, child map per coarse site."""
+
+    def __init__(self, s, fine, coarse, parent, off):
+        self.s, self.K, self.fine, self.coarse, self.parent, self.off = s, s ** 3, fine, coarse, parent, off
+        self.child = None
+        self.pairs = None
+
+    def child_map(self):
+        if self.child is None:
+            dev = self.parent.device
+            self.child = torch.empty((self.coarse.n, self.K), dtype=torch.int32, device=dev)
+            st = _lib.stream_for(self.parent)
+            check(lib.b200scn_child_map(ptr(self.parent), ptr(self.off), self.fine.n, None, self.K,
+                                        ptr(self.child), self.coarse.n, st))
+        return self.child
+
+    def child_pairs(self):
+        """pair_in = fine ids, pair_out = coarse ids, grouped by offset."""
+        if self.pairs is None:
+            self.pairs = build_pairs(self.child_map(), self.coarse.n, self.K, self.fine.n)
+        return self.pairs
+
+
+class Metadata:
+    def __init__(self, dimension=3):
+        self.dimension = dimension
+        self.levels = {}   # spatial size -> Level
+        self.downs = {}    # (fine size, s) -> Down
+        self.P = 0
+        self.mode = 4
+        self.pv = self.count = self.first_row = self.last_row = None
+        self.syncs = 0     # host synchronisations this forward (diagnostic)
+
+    # ------------------------------------------------------------------ InputLayer
+    def build_input(self, coords, spatial_size, mode, device):
+        """coords (P,3|4) int64 on any device -> level-0 grid (+ speculative strided pyramid)."""
+        if coords.dim() != 2 or coords.shape[1] not in (3, 4):
+            raise ValueError("InputLayer: coords must be (N,3) or (N,4), got %s" % (tuple(coords.shape),))
+        coords = coords.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+        P = coords.shape[0]
+        self.P, self.mode = P, mode
+        st = _lib.stream_for(coords)
+        i32, i64 = torch.int32, torch.int64
+        keys = torch.empty(max(P, 1), dtype=i64, device=device)
+        s_hint, depth = _pyramid_hint
+        sizes = [int(spatial_size)]
+        while len(sizes) <= depth and sizes[-1] % s_hint == 0 and sizes[-1] // s_hint >= 1 and sizes[-1] > 1:
+            sizes.append(sizes[-1] // s_hint)
+        nlev = len(sizes)
+        # header: [err, n_0, n_1, ..., n_{nlev-1}]
+        hdr = torch.zeros(1 + nlev, dtype=i32, device=device)
+        check(lib.b200scn_pack_coords(ptr(coords), P, coords.shape[1], int(spatial_size), ptr(keys), ptr(hdr), st))
+        cap = lib.b200scn_hash_capacity(P)
+        sbytes = lib.b200scn_grid_scratch_bytes(P)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=device)
+        self.pv = torch.empty(max(P, 1), dtype=i32, device=device)
+        self.first_row = torch.empty(max(P, 1), dtype=i32, device=device)
+        self.last_row = torch.empty(max(P, 1), dtype=i32, device=device)
+        self.count = torch.empty(max(P, 1), dtype=i32, device=device)
+        raw = []
+        ukeys = torch.empty(max(P, 1), dtype=i64, device=device)
+        hkeys = torch.empty(cap, dtype=i64, device=device)
+        hvals = torch.empty(cap, dtype=i32, device=device)
+        check(lib.b200scn_grid_build(ptr(keys), P, None, ptr(hkeys), ptr(hvals), cap, ptr(self.pv), ptr(ukeys),
+                                     ptr(self.first_row), ptr(self.last_row), ptr(self.count),
+                                     hdr[1:].data_ptr(), ptr(scratch), sbytes, st))
+        raw.append((ukeys, hkeys, hvals, None, None))
+        for li in range(1, nlev):
+            fu = raw[-1][0]
+            ckeys = keys  # reuse: the packed point keys are dead after the level-0 build
+            off = torch.empty(max(P, 1), dtype=torch.uint8, device=device)
+            parent = torch.empty(max(P, 1), dtype=i32, device=device)
+            n_dev = hdr[li:].data_ptr()
+            check(lib.b200scn_coarse_keys(ptr(fu), P, n_dev, s_hint, ptr(ckeys), ptr(off), st))
+            cu = torch.empty(max(P, 1), dtype=i64, device=device)
+            ck = torch.empty(cap, dtype=i64, device=device)
+            cv = torch.empty(cap, dtype=i32, device=device)
+            check(lib.b200scn_grid_build(ptr(ckeys), P, n_dev, ptr(ck), ptr(cv), cap, ptr(parent), ptr(cu),
+                                         None, None, None, hdr[li + 1:].data_ptr(), ptr(scratch), sbytes, st))
+            raw.append((cu, ck, cv, parent, off))
+        host = hdr.cpu()  # the one host sync of the forward
+        self.syncs += 1
+        if int(host[0]) != 0:
+            raise ValueError("InputLayer: coordinates outside [0, %d) or bad sample index" % int(spatial_size))
+        counts = [int(v) for v in host[1:]]
+        for li, size in enumerate(sizes):
+            u, hk, hv, parent, off = raw[li]
+            n = counts[li]
+            lvl = Level(size, n, u[:n], hk, hv, cap)
+            self.levels[size] = lvl
+            if li > 0:
+                fine = self.levels[sizes[li - 1]]
+                self.downs[(sizes[li - 1], s_hint)] = Down(s_hint, fine, lvl, parent[:fine.n], off[:fine.n])
+        n0 = counts[0]
+        self.pv, self.count = self.pv[:P], self.count[:n0]
+        self.first_row, self.last_row = self.first_row[:n0], self.last_row[:n0]
+        return self.levels[sizes[0]]
+
+    # ------------------------------------------------------------------ strided levels on demand
+    def get_down(self, size, s):
+        key = (size, s)
+        if key not in self.downs:
+            if size % s != 0:
+                raise ValueError("Convolution: spatial size %d not divisible by stride %d" % (size, s))
+            fine = self.levels[size]
+            device = fine.ukeys.device
+            st = _lib.stream_for(fine.ukeys)
+            n = fine.n
+            i32, i64 = torch.int32, torch.int64
+            ckeys = torch.empty(max(n, 1), dtype=i64, device=device)
+            off = torch.empty(max(n, 1), dtype=torch.uint8, device=device)
+            parent = torch.empty(max(n, 1), dtype=i32, device=device)
+            cu = torch.empty(max(n, 1), dtype=i64, device=device)
+            cap = lib.b200scn_hash_capacity(n)
+            ck = torch.empty(cap, dtype=i64, device=device)
+            cv = torch.empty(cap, dtype=i32, device=device)
+            cnt = torch.zeros(1, dtype=i32, device=device)
+            sbytes = lib.b200scn_grid_scratch_bytes(n)
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=device)
+            check(lib.b200scn_coarse_keys(ptr(fine.ukeys), n, None, s, ptr(ckeys), ptr(off), st))
+            check(lib.b200scn_grid_build(ptr(ckeys), n, None, ptr(ck), ptr(cv), cap, ptr(parent), ptr(cu),
+                                         None, None, None, ptr(cnt), ptr(scratch), sbytes, st))
+            nc = int(cnt.cpu()[0])
+            self.syncs += 1
+            csize = (size - s) // s + 1
+            coarse = self.levels.get(csize)
+            if coarse is None or coarse.n != nc:
+                # scn registers one grid per spatial size; a second, different grid of the same size can
+                # only come from mixing stride chains, which the reference's nets never do
+                if coarse is not None:
+                    raise ValueError("two different grids for spatial size %d" % csize)
+                coarse = Level(csize, nc, cu[:nc], ck, cv, cap)
+                self.levels[csize] = coarse
+            self.downs[key] = Down(s, fine, coarse, parent[:n], off[:n])
+        return self.downs[key]
+
+    def get_up(self, coarse_size, s):
+        """The (fine, coarse) relation whose coarse side has `coarse_size` (Deconvolution / UnPooling reuse the
+        rulebook built on the way down)."""
+        fsize = (coarse_size - 1) * s + s
+        key = (fsize, s)
+        if key not in self.downs:
+            raise ValueError("Deconvolution/UnPooling to spatial size %d: no matching Convolution was run" % fsize)
+        return self.downs[key]

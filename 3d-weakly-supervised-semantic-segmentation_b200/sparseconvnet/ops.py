@@ -1,0 +1,271 @@
+"""Autograd functions over the b200scn C ABI.  One forward / backward-input / backward-weight launch per layer.
+
+Each function cites the upstream scn entry point it replaces and the reference call site that
+reaches it.  All tensors are CUDA fp32; there is no CPU path.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+# 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05) where the kernel supports the shape
+_precision = [0]
+
+
+def set_precision(name):
+    """'fp32' (exact-fp32 CUDA cores) or 'tf32' (tcgen05 TF32 tiles, rel 1e-3 tolerance)."""
+    _precision[0] = {"fp32": 0, "tf32": 1}[name]
+
+
+def get_precision():
+    return "tf32" if _precision[0] else "fp32"
+
+
+def _c(t):
+    """fp32 contiguous-rows view: returns (tensor, leading dimension)."""
+    if t.dtype != torch.float32:
+        raise TypeError("b200scn computes in fp32; got %s" % t.dtype)
+    if t.dim() != 2 or t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def gather_conv(x, map_t, n_out, K, w, addend=None):
+    """out[o] = sum_k x[map[o,k]] @ w[k] (+ addend[o]);  w (K,Cin,Cout)."""
+    x, ldx = _c(x)
+    w = w.contiguous()
+    Cin, Cout = w.shape[1], w.shape[2]
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    lda = 0
+    if addend is not None:
+        addend, lda = _c(addend)
+    check(lib.b200scn_gather_conv(ptr(x), ldx, ptr(map_t), n_out, K, ptr(w), Cin, Cout, ptr(addend), lda,
+                                  ptr(out), Cout, _precision[0], _lib.stream_for(x)))
+    return out
+
+
+def scatter_conv(x, map_t, n_out, K, w):
+    """out[map[j,k]] = x[j] @ w[k]; every out row is addressed exactly once by a strided child map."""
+    x, ldx = _c(x)
+    w = w.contiguous()
+    Cin, Cout = w.shape[1], w.shape[2]
+    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    check(lib.b200scn_scatter_conv(ptr(x), ldx, ptr(map_t), x.shape[0], K, ptr(w), Cin, Cout, ptr(out), Cout,
+                                   _precision[0], _lib.stream_for(x)))
+    return out
+
+
+def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max):
+    """dW[k] = sum_p a[pair_a[p]]^T (x) g[pair_g[p]] over list k."""
+    a, lda = _c(a)
+    g, ldg = _c(g)
+    Ca, Cg = a.shape[1], g.shape[1]
+    dw = torch.empty((K, Ca, Cg), dtype=torch.float32, device=a.device)
+    check(lib.b200scn_pair_dw(ptr(a), lda, ptr(g), ldg, ptr(pair_a), ptr(pair_g), ptr(offsets), K, n_pairs_max,
+                              Ca, Cg, ptr(dw), _precision[0], _lib.stream_for(a)))
+    return dw
+
+
+class SubmanifoldConvFn(torch.autograd.Function):
+    """scn.SubmanifoldConvolution (models/SparseConvNet.py:62,117,119): replaces upstream
+    SubmanifoldConvolution_updateOutput / _backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, level):
+        nbr = level.subm_map()
+        ctx.level = level
+        ctx.save_for_backward(x, w)
+        return gather_conv(x, nbr, level.n, 27, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        level = ctx.level
+        dx = dw = None
+        g = g.contiguous()
+        if ctx.needs_input_grad[0]:
+            # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
+            wt = w.flip(0).transpose(1, 2).contiguous()
+            dx = gather_conv(g, level.subm_map(), level.n, 27, wt)
+        if ctx.needs_input_grad[1]:
+            pin, pout, offs = level.subm_pairs()
+            dw = pair_dw(x, g, pin, pout, offs, 27, level.n)
+        return dx, dw, None
+
+
+class ConvolutionFn(torch.autograd.Function):
+    """scn.Convolution size==stride (models/SparseConvNet.py:137-138): Convolution_updateOutput / _backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, down):
+        ctx.down = down
+        ctx.save_for_backward(x, w)
+        return gather_conv(x, down.child_map(), down.coarse.n, down.K, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        down = ctx.down
+        dx = dw = None
+        g = g.contiguous()
+        if ctx.needs_input_grad[0]:
+            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, w.transpose(1, 2).contiguous())
+        if ctx.needs_input_grad[1]:
+            pin, pout, offs = down.child_pairs()
+            dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n)
+        return dx, dw, None
+
+
+class DeconvolutionFn(torch.autograd.Function):
+    """scn.Deconvolution (inside scn.UNet, models/SparseConvNet.py:63-68): Deconvolution_updateOutput / _backward,
+    on the rulebook the matching Convolution built, roles swapped."""
+
+    @staticmethod
+    def forward(ctx, x, w, down):
+        ctx.down = down
+        ctx.save_for_backward(x, w)
+        return scatter_conv(x, down.child_map(), down.fine.n, down.K, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        down = ctx.down
+        dx = dw = None
+        g = g.contiguous()
+        if ctx.needs_input_grad[0]:
+            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, w.transpose(1, 2).contiguous())
+        if ctx.needs_input_grad[1]:
+            pin, pout, offs = down.child_pairs()
+            dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n)
+        return dx, dw, None
+
+
+class UnPoolingFn(torch.autograd.Function):
+    """scn.UnPooling (models/SparseConvNet.py:140,193): UnPooling_updateOutput / _updateGradInput."""
+
+    @staticmethod
+    def forward(ctx, x, down):
+        ctx.down = down
+        x, ldx = _c(x)
+        C = x.shape[1]
+        out = torch.empty((down.fine.n, C), dtype=torch.float32, device=x.device)
+        check(lib.b200scn_unpool(ptr(x), ldx, ptr(down.parent), down.fine.n, C, ptr(out), C, _lib.stream_for(x)))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        down = ctx.down
+        g, ldg = _c(g)
+        C = g.shape[1]
+        dx = torch.empty((down.coarse.n, C), dtype=torch.float32, device=g.device)
+        check(lib.b200scn_unpool_bwd(ptr(g), ldg, ptr(down.child_map()), down.coarse.n, down.K, C, ptr(dx), C,
+                                     _lib.stream_for(g)))
+        return dx, None
+
+
+class NetworkInNetworkFn(torch.autograd.Function):
+    """scn.NetworkInNetwork (models/SparseConvNet.py:114): NetworkInNetwork_updateOutput / updateGradInput /
+    accGradParameters -- a one-offset convolution with the identity rulebook."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return gather_conv(x, None, x.shape[0], 1, w.unsqueeze(0))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        g = g.contiguous()
+        if ctx.needs_input_grad[0]:
+            dx = gather_conv(g, None, g.shape[0], 1, w.t().contiguous().unsqueeze(0))
+        if ctx.needs_input_grad[1]:
+            dw = pair_dw(x, g, None, None, None, 1, x.shape[0])[0]
+        return dx, dw
+
+
+class BatchNormFn(torch.autograd.Function):
+    """scn.BatchNormReLU / BatchNormLeakyReLU (models/SparseConvNet.py:69,116,118,136):
+    BatchNormalization_updateOutput / _backward (eps 1e-4, momentum 0.9 on the old value, App. B.8)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak):
+        x, ldx = _c(x)
+        n, C = x.shape
+        dev = x.device
+        y = torch.empty((n, C), dtype=torch.float32, device=dev)
+        save_mean = torch.empty(C, dtype=torch.float32, device=dev)
+        save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        check(lib.b200scn_bn_forward(ptr(x), ldx, n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
+                                     ptr(save_mean), ptr(save_invstd), eps, momentum, 1 if train else 0, leak,
+                                     ptr(y), C, ptr(scratch), _lib.stream_for(x)))
+        ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
+        ctx.leak = leak
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
+        x, ldx = _c(x)
+        g, ldg = _c(g)
+        n, C = x.shape
+        dev = x.device
+        dx = torch.empty((n, C), dtype=torch.float32, device=dev)
+        dweight = torch.empty(C, dtype=torch.float32, device=dev)
+        dbias = torch.empty(C, dtype=torch.float32, device=dev)
+        scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        check(lib.b200scn_bn_backward(ptr(x), ldx, ptr(g), ldg, n, C, ptr(weight), ptr(bias), ptr(save_mean),
+                                      ptr(save_invstd), ctx.leak, ptr(dx), C, ptr(dweight), ptr(dbias),
+                                      ptr(scratch), _lib.stream_for(x)))
+        return dx, dweight, dbias, None, None, None, None, None, None
+
+
+class InputFeaturesFn(torch.autograd.Function):
+    """scn.InputLayer feature half (models/SparseConvNet.py:61): InputLayer_updateOutput / _updateGradInput."""
+
+    @staticmethod
+    def forward(ctx, feats, md, n0):
+        feats = feats.contiguous()
+        if feats.dtype != torch.float32:
+            raise TypeError("InputLayer: features must be float32, got %s" % feats.dtype)
+        P, C = feats.shape
+        out = torch.zeros((n0, C), dtype=torch.float32, device=feats.device)
+        check(lib.b200scn_input_features(ptr(feats), P, C, ptr(md.pv), ptr(md.count), ptr(md.first_row),
+                                         ptr(md.last_row), md.mode, ptr(out), _lib.stream_for(feats)))
+        ctx.md = md
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        md = ctx.md
+        g = g.contiguous()
+        C = g.shape[1]
+        d = torch.empty((md.P, C), dtype=torch.float32, device=g.device)
+        check(lib.b200scn_input_features_bwd(ptr(g), md.P, C, ptr(md.pv), ptr(md.count), ptr(md.first_row),
+                                             ptr(md.last_row), md.mode, ptr(d), _lib.stream_for(g)))
+        return d, None, None
+
+
+class OutputFeaturesFn(torch.autograd.Function):
+    """scn.OutputLayer (models/SparseConvNet.py:70): OutputLayer_updateOutput / _updateGradInput."""
+
+    @staticmethod
+    def forward(ctx, feats, md):
+        feats, ldf = _c(feats)
+        C = feats.shape[1]
+        out = torch.empty((md.P, C), dtype=torch.float32, device=feats.device)
+        check(lib.b200scn_output_features(ptr(feats), ldf, md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
+                                          md.mode, ptr(out), _lib.stream_for(feats)))
+        ctx.md, ctx.n = md, feats.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        md = ctx.md
+        g = g.contiguous()
+        C = g.shape[1]
+        d = torch.zeros((ctx.n, C), dtype=torch.float32, device=g.device)
+        check(lib.b200scn_output_features_bwd(ptr(g), md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
+                                              md.mode, ptr(d), C, _lib.stream_for(g)))
+        return d, None

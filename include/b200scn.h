@@ -1,0 +1,155 @@
+/*
+ * b200scn.h -- C ABI of the B200-native sparse voxel convolution backbone.
+ *
+ * Drop-in boundary for the `sparseconvnet` ("scn") operator layer that the reference's encoders
+ * compose (models/SparseConvNet.py:5,59-71,73-88,107-158).  Upstream scn binds a pybind module
+ * `sparseconvnet.SCN` whose entry points take ATen tensors; every function below
+ * replaces one of those, with plain device pointers, sizes in elements, leading dimensions in
+ * elements and an opaque `cudaStream_t` passed as `void*`.  No torch/ATen type crosses this ABI.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - every call only enqueues work on `stream` and never synchronises;
+ *  - return value 0 = ok, nonzero = error (text via b200scn_last_error());
+ *  - `n_dev` arguments: optional device int32 holding the live row count when the host only knows an
+ *    upper bound `n_max` (rulebook pyramids are built without host round trips); NULL means n_max is exact;
+ *  - site key layout: b<<48 | x<<32 | y<<16 | z  (x,y,z < 65536, sample index b < 32768);
+ *  - feature maps are fp32 row-major (rows = active sites, ids in first-occurrence order).
+ */
+#ifndef B200SCN_H
+#define B200SCN_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *b200scn_last_error(void);
+int b200scn_version(void);
+/* bind the calling thread of this library's CUDA runtime to `device` (one process per GPU) */
+int b200scn_set_device(int device);
+/* number of kernels this library has enqueued since load (bench.py's gpu_launches) */
+unsigned long long b200scn_launch_count(void);
+
+/* ------------------------------------------------------------------ grids / rulebooks (A1-A4) */
+/* hash slots for n keys (power of two >= 2n) */
+int64_t b200scn_hash_capacity(int64_t n);
+/* scratch bytes b200scn_grid_build needs for n_max rows */
+size_t b200scn_grid_scratch_bytes(int64_t n_max);
+
+/* scn.InputLayer coordinate intake (models/SparseConvNet.py:61; dataset/data.py:186,198):
+ * coords (P,ncols) int64 [x,y,z(,b)] -> keys[P]; *err_flag |= 1 if any coordinate is outside
+ * [0,spatial_size) or the sample index is negative / too large. */
+int b200scn_pack_coords(const int64_t *coords, int64_t P, int ncols, int64_t spatial_size,
+                        uint64_t *keys, int32_t *err_flag, void *stream);
+
+/* Active-site numbering (upstream Metadata::inputLayer / Convolution_InputSgsToRulesAndOutputSgs):
+ * unique keys get ids in order of first occurrence.  hkeys/hvals: hash table of `cap` slots (the call
+ * initialises it); id_of_row[n_max]; ukeys[n_max] keys in id order; first_row/last_row/count[n_max] are
+ * optional per-site statistics (NULL to skip); n_unique_dev receives the number of sites. */
+int b200scn_grid_build(const uint64_t *keys, int64_t n_max, const int32_t *n_dev, uint64_t *hkeys,
+                       int32_t *hvals, int64_t cap, int32_t *id_of_row, uint64_t *ukeys,
+                       int32_t *first_row, int32_t *last_row, int32_t *count,
+                       int32_t *n_unique_dev, void *scratch, size_t scratch_bytes, void *stream);
+
+/* Strided grid, filter size == stride == s (scn.Convolution(3,a,b,s,s), models/SparseConvNet.py:137):
+ * ckeys[i] = key of site//s, off[i] = ((x%s)*s+(y%s))*s+(z%s). */
+int b200scn_coarse_keys(const uint64_t *ukeys, int64_t n_max, const int32_t *n_dev, int s,
+                        uint64_t *ckeys, uint8_t *off, void *stream);
+
+/* Submanifold 3x3x3 neighbour table (upstream SubmanifoldConvolution_SgsToRules):
+ * nbr[o*27+k] = id of site o+d_k (k = 9(dx+1)+3(dy+1)+(dz+1)) or -1; counts27_dev[k] += #present. */
+int b200scn_subm_map(const uint64_t *ukeys, int64_t n_max, const int32_t *n_dev,
+                     const uint64_t *hkeys, const int32_t *hvals, int64_t cap, int64_t spatial_size,
+                     int32_t *nbr, int32_t *counts27_dev, void *stream);
+
+/* child[j*K+off[i]] = i for every fine site i with parent[i] == j; other entries -1. */
+int b200scn_child_map(const int32_t *parent, const uint8_t *off, int64_t nf_max,
+                      const int32_t *nf_dev, int K, int32_t *child, int64_t nc_max, void *stream);
+
+/* scn-form rulebook: compact map[n][K] (-1 = absent) into per-offset pair lists, ascending row:
+ * for k: pairs p in [offsets[k], offsets[k+1]) : pair_in[p] = map[row][k], pair_out[p] = row.
+ * offsets_dev has K+1 entries.  scratch: b200scn_pair_scratch_bytes(n,K). */
+size_t b200scn_pair_scratch_bytes(int64_t n, int K);
+int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, int32_t *pair_out,
+                       int32_t *offsets_dev, void *scratch, size_t scratch_bytes, void *stream);
+
+/* ------------------------------------------------------------------ convolutions (A5-A7, A10) */
+/* out[o,:] = sum_k A[map[o*K+k],:] . W[k]  (+ addend[o,:] if addend)      W: (K,Cin,Cout) row-major.
+ * map NULL => K must be 1 and row o reads A[o] (NetworkInNetwork).
+ * Replaces SubmanifoldConvolution_updateOutput / Convolution_updateOutput and, with the transposed
+ * mirrored weights, SubmanifoldConvolution / Deconvolution backward-input.
+ * precision: 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05). */
+int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K,
+                        const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
+                        float *out, int64_t ldo, int precision, void *stream);
+
+/* out[map[j*K+k],:] = A[j,:] . W[k] for every present (j,k)   (Deconvolution_updateOutput,
+ * Convolution backward-input).  Rows of `out` not addressed by map are left untouched. */
+int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,
+                         const float *W, int Cin, int Cout, float *out, int64_t ldo, int precision,
+                         void *stream);
+
+/* dW[k] = sum over pairs p of list k of A[pair_a[p],:]^T (x) G[pair_g[p],:]   (K,Ca,Cg) row-major.
+ * pair_a / pair_g NULL => identity (row p).  offsets_dev NULL => one list [0,n_pairs_max).
+ * n_pairs_max bounds the length of any single list.  dW is overwritten. */
+int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                    const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max,
+                    int Ca, int Cg, float *dW, int precision, void *stream);
+
+/* out[i,:] = in[parent[i],:]  (UnPooling_updateOutput) and its transpose via the child map. */
+int b200scn_unpool(const float *in, int64_t ldi, const int32_t *parent, int64_t n_fine, int C,
+                   float *out, int64_t ldo, void *stream);
+int b200scn_unpool_bwd(const float *d_out, int64_t ldd, const int32_t *child, int64_t n_coarse, int K,
+                       int C, float *d_in, int64_t ldi, void *stream);
+
+/* ------------------------------------------------------------------ BatchNormReLU (A8) */
+/* BatchNormalization_updateOutput: train!=0 => batch statistics over the n rows (biased var), running
+ * stats updated as r = momentum*r + (1-momentum)*batch (unbiased var); else running stats.
+ * y = leaky_relu((x-mean)*invstd*weight+bias, leak).  scratch: 2*C doubles. */
+int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const float *weight,
+                       const float *bias, float *running_mean, float *running_var, float *save_mean,
+                       float *save_invstd, float eps, float momentum, int train, float leak,
+                       float *y, int64_t ldy, double *scratch, void *stream);
+/* BatchNormalization_backward (batch-statistics formula; the ReLU mask is recomputed from x, which
+ * equals the sign of the forward output bit for bit). scratch: 2*C doubles. */
+int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
+                        const float *weight, const float *bias, const float *save_mean,
+                        const float *save_invstd, float leak, float *dx, int64_t lddx,
+                        float *d_weight, float *d_bias, double *scratch, void *stream);
+
+/* ------------------------------------------------------------------ I/O layers (A1, A9) */
+/* InputLayer_updateOutput feature half: out[pv[r]] += mult(r)*feats[r]; mode 1 last, 2 first, 3 sum,
+ * 4 mean (Function_test.py:38-44).  out must be zeroed by the caller. */
+int b200scn_input_features(const float *feats, int64_t P, int C, const int32_t *pv,
+                           const int32_t *count, const int32_t *first_row, const int32_t *last_row,
+                           int mode, float *out, void *stream);
+int b200scn_input_features_bwd(const float *d_out, int64_t P, int C, const int32_t *pv,
+                               const int32_t *count, const int32_t *first_row,
+                               const int32_t *last_row, int mode, float *d_in, void *stream);
+/* OutputLayer_updateOutput: out[r,:] = feats[pv[r],:] (no averaging); backward sums rows per site
+ * (d_feats must be zeroed by the caller). */
+int b200scn_output_features(const float *feats, int64_t ldf, int64_t P, int C, const int32_t *pv,
+                            const int32_t *first_row, const int32_t *last_row, int mode, float *out,
+                            void *stream);
+int b200scn_output_features_bwd(const float *d_out, int64_t P, int C, const int32_t *pv,
+                                const int32_t *first_row, const int32_t *last_row, int mode,
+                                float *d_feats, int64_t ldf, void *stream);
+
+/* ------------------------------------------------------------------ point2mask (A12) */
+/* ops/point2mask/_ext_src/src/ball_query.cpp:8-33 (+ ball_query_gpu.cu:9-45). idx is fully written
+ * (-1 sentinel included). */
+int b200scn_p2m_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xy,
+                           const float *xy, const int32_t *pointnums, int32_t *idx, void *stream);
+/* ops/point2mask/_ext_src/src/group_points.cpp:12-36 / 38-62. out / grad_points fully written. */
+int b200scn_p2m_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                             const int32_t *idx, float *out, void *stream);
+int b200scn_p2m_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                                  const float *grad_out, const int32_t *idx, float *grad_points,
+                                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

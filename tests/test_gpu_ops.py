@@ -1,0 +1,107 @@
+"""Each sparse op on the GPU vs the CPU oracle (fp32 path: rel 1e-4; the tolerance north_star states is 1e-3)."""
+import pytest
+import torch
+
+from _util import copy_params, random_cloud, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _pair(coords, feats, nfeat):
+    import sparseconvnet as scn
+    from oracle import scn_oracle as ref
+    torch.manual_seed(0)
+    f = torch.randn(coords.shape[0], nfeat)
+    fg = f.clone().cuda().requires_grad_(True)
+    fr = f.clone().requires_grad_(True)
+    xg = scn.InputLayer(3, 4096, mode=4)([coords, fg])
+    xr = ref.InputLayer(3, 4096, mode=4)([coords, fr])
+    return scn, ref, xg, xr, fg, fr
+
+
+def _check(mg, mr, xg, xr, fg, fr, dense_out=False):
+    copy_params(mr, mg)
+    mg.cuda()
+    yg, yr = mg(xg), mr(xr)
+    og = yg if dense_out else yg.features
+    o_r = yr if dense_out else yr.features
+    assert og.shape == o_r.shape
+    assert rel_err(og, o_r) < TOL
+    torch.manual_seed(1)
+    go = torch.randn_like(o_r)
+    og.backward(go.cuda())
+    o_r.backward(go)
+    assert rel_err(fg.grad, fr.grad) < TOL
+    for (n, pg), (_, pr) in zip(mg.named_parameters(), mr.named_parameters()):
+        assert pg.grad is not None, n
+        assert rel_err(pg.grad, pr.grad) < TOL, n
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 16), (16, 16), (32, 32), (48, 80), (64, 32), (5, 7)])
+def test_submanifold_conv(cin, cout):
+    coords, feats = random_cloud(cin * 100 + cout, 3000, 24, 2)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
+    _check(scn.SubmanifoldConvolution(3, cin, cout, 3, False), ref.SubmanifoldConvolution(3, cin, cout, 3, False), xg, xr, fg, fr)
+
+
+@pytest.mark.parametrize("cin,cout,s", [(16, 32, 2), (32, 48, 2), (16, 24, 4), (6, 10, 2)])
+def test_strided_conv_deconv_unpool(cin, cout, s):
+    coords, feats = random_cloud(cin + cout + s, 4000, 30, 2)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
+    mg = scn.Sequential(scn.Convolution(3, cin, cout, s, s, False), scn.Deconvolution(3, cout, cin, s, s, False))
+    mr = ref.Sequential(ref.Convolution(3, cin, cout, s, s, False), ref.Deconvolution(3, cout, cin, s, s, False))
+    _check(mg, mr, xg, xr, fg, fr)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
+    mg = scn.Sequential(scn.Convolution(3, cin, cout, s, s, False), scn.UnPooling(3, s, s))
+    mr = ref.Sequential(ref.Convolution(3, cin, cout, s, s, False), ref.UnPooling(3, s, s))
+    _check(mg, mr, xg, xr, fg, fr)
+
+
+@pytest.mark.parametrize("c,leak", [(16, 0.0), (32, 0.0), (112, 0.333), (448, 0.0), (6, 0.0)])
+def test_batchnorm(c, leak):
+    coords, feats = random_cloud(c, 5000, 40, 2)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, c)
+    mg, mr = scn.BatchNormLeakyReLU(c, leakiness=leak), ref.BatchNormLeakyReLU(c, leakiness=leak)
+    with torch.no_grad():
+        mr.weight.uniform_(0.5, 1.5)
+        mr.bias.uniform_(-0.5, 0.5)
+    _check(mg, mr, xg, xr, fg, fr)
+    assert rel_err(mg.running_mean, mr.running_mean) < 1e-5
+    assert rel_err(mg.running_var, mr.running_var) < 1e-5
+    # eval mode uses the running statistics
+    mg.eval(), mr.eval()
+    assert rel_err(mg(xg).features, mr(xr).features) < TOL
+
+
+@pytest.mark.parametrize("a,b", [(64, 32), (32, 64), (7, 5)])
+def test_network_in_network_and_tables(a, b):
+    coords, feats = random_cloud(a + b, 3000, 24, 2)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, a)
+
+    def net(ns):
+        return ns.Sequential(
+            ns.ConcatTable().add(ns.NetworkInNetwork(a, b, False)).add(
+                ns.Sequential(ns.BatchNormReLU(a), ns.SubmanifoldConvolution(3, a, b, 3, False))),
+            ns.AddTable(),
+            ns.ConcatTable().add(ns.Identity()).add(ns.NetworkInNetwork(b, a, False)),
+            ns.JoinTable())
+    _check(net(scn), net(ref), xg, xr, fg, fr)
+
+
+def test_output_layer_and_counters():
+    import sparseconvnet as scn
+    from oracle import scn_oracle as ref
+    coords, feats = random_cloud(3, 2500, 16, 2, dup_frac=0.5)
+    scn_, ref_, xg, xr, fg, fr = _pair(coords, feats, 8)
+    scn.forward_pass_multiplyAdd_count = 0
+    scn.forward_pass_hidden_states = 0
+    ref.forward_pass_multiplyAdd_count = 0
+    ref.forward_pass_hidden_states = 0
+    mg = scn.Sequential(scn.SubmanifoldConvolution(3, 8, 12, 3, False), scn.Convolution(3, 12, 6, 2, 2, False),
+                        scn.NetworkInNetwork(6, 4, False), scn.UnPooling(3, 2, 2), scn.OutputLayer(3))
+    mr = ref.Sequential(ref.SubmanifoldConvolution(3, 8, 12, 3, False), ref.Convolution(3, 12, 6, 2, 2, False),
+                        ref.NetworkInNetwork(6, 4, False), ref.UnPooling(3, 2, 2), ref.OutputLayer(3))
+    _check(mg, mr, xg, xr, fg, fr, dense_out=True)
+    assert scn.forward_pass_multiplyAdd_count == ref.forward_pass_multiplyAdd_count
+    assert scn.forward_pass_hidden_states == ref.forward_pass_hidden_states
