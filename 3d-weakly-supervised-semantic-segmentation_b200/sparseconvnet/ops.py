@@ -21,6 +21,47 @@ def get_precision():
     return "tf32" if _precision[0] else "fp32"
 
 
+# ---- optional per-launch timing for bench.py's roofline block (CUDA events on the launching stream)
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {kind: {ms, n, bytes, flops, kernel}}; algorithmic bytes/flops per SURVEY 8d (fp32 rows touched once,
+    8 B per rule pair, weights once)."""
+    global _prof
+    recs, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for kind, kernel, nrows_bytes, rules, per_rule_bytes, flops_per_rule, e0, e1 in recs:
+        r = sum(rules.rule_counts()) if hasattr(rules, "rule_counts") else int(rules)
+        d = out.setdefault(kind, {"ms": 0.0, "n": 0, "bytes": 0.0, "flops": 0.0, "kernel": kernel})
+        d["ms"] += e0.elapsed_time(e1)
+        d["n"] += 1
+        d["bytes"] += nrows_bytes + per_rule_bytes * r
+        d["flops"] += flops_per_rule * r
+    return out
+
+
+def _p0(kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule):
+    if _prof is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return (kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule, e0)
+
+
+def _p1(tok):
+    if tok is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _prof.append(tok + (e1,))
+
+
 def _c(t):
     """fp32 contiguous-rows view: returns (tensor, leading dimension)."""
     if t.dtype != torch.float32:
@@ -30,8 +71,8 @@ def _c(t):
     return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
 
 
-def gather_conv(x, map_t, n_out, K, w, addend=None):
-    """out[o] = sum_k x[map[o,k]] @ w[k] (+ addend[o]);  w (K,Cin,Cout)."""
+def gather_conv(x, map_t, n_out, K, w, addend=None, rules=None):
+    """out[o] = sum_k x[map[o,k]] @ w[k] (+ addend[o]);  w (K,Cin,Cout).  `rules`: rule count (or Level) for accounting."""
     x, ldx = _c(x)
     w = w.contiguous()
     Cin, Cout = w.shape[1], w.shape[2]
@@ -39,8 +80,11 @@ def gather_conv(x, map_t, n_out, K, w, addend=None):
     lda = 0
     if addend is not None:
         addend, lda = _c(addend)
+    tok = _p0("gather%d" % K, "conv_gather", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
+              n_out if rules is None else rules, 8.0 if map_t is not None else 0.0, 2.0 * Cin * Cout)
     check(lib.b200scn_gather_conv(ptr(x), ldx, ptr(map_t), n_out, K, ptr(w), Cin, Cout, ptr(addend), lda,
                                   ptr(out), Cout, _precision[0], _lib.stream_for(x)))
+    _p1(tok)
     return out
 
 
@@ -50,19 +94,25 @@ def scatter_conv(x, map_t, n_out, K, w):
     w = w.contiguous()
     Cin, Cout = w.shape[1], w.shape[2]
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    tok = _p0("scatter%d" % K, "conv_scatter", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
+              n_out, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_scatter_conv(ptr(x), ldx, ptr(map_t), x.shape[0], K, ptr(w), Cin, Cout, ptr(out), Cout,
                                    _precision[0], _lib.stream_for(x)))
+    _p1(tok)
     return out
 
 
-def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max):
+def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max, rules=None):
     """dW[k] = sum_p a[pair_a[p]]^T (x) g[pair_g[p]] over list k."""
     a, lda = _c(a)
     g, ldg = _c(g)
     Ca, Cg = a.shape[1], g.shape[1]
     dw = torch.empty((K, Ca, Cg), dtype=torch.float32, device=a.device)
+    tok = _p0("pair_dw%d" % K, "pair_dw", 4.0 * (a.shape[0] * Ca + g.shape[0] * Cg) + 4.0 * K * Ca * Cg,
+              n_pairs_max if rules is None else rules, 8.0 if pair_a is not None else 0.0, 2.0 * Ca * Cg)
     check(lib.b200scn_pair_dw(ptr(a), lda, ptr(g), ldg, ptr(pair_a), ptr(pair_g), ptr(offsets), K, n_pairs_max,
                               Ca, Cg, ptr(dw), _precision[0], _lib.stream_for(a)))
+    _p1(tok)
     return dw
 
 
@@ -75,7 +125,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
         nbr = level.subm_map()
         ctx.level = level
         ctx.save_for_backward(x, w)
-        return gather_conv(x, nbr, level.n, 27, w)
+        return gather_conv(x, nbr, level.n, 27, w, rules=level)
 
     @staticmethod
     def backward(ctx, g):
@@ -86,10 +136,10 @@ class SubmanifoldConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
             wt = w.flip(0).transpose(1, 2).contiguous()
-            dx = gather_conv(g, level.subm_map(), level.n, 27, wt)
+            dx = gather_conv(g, level.subm_map(), level.n, 27, wt, rules=level)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = level.subm_pairs()
-            dw = pair_dw(x, g, pin, pout, offs, 27, level.n)
+            dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
         return dx, dw, None
 
 
@@ -100,7 +150,7 @@ class ConvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return gather_conv(x, down.child_map(), down.coarse.n, down.K, w)
+        return gather_conv(x, down.child_map(), down.coarse.n, down.K, w, rules=down.fine.n)
 
     @staticmethod
     def backward(ctx, g):
@@ -112,7 +162,7 @@ class ConvolutionFn(torch.autograd.Function):
             dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, w.transpose(1, 2).contiguous())
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
-            dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n)
+            dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
         return dx, dw, None
 
 
@@ -133,10 +183,10 @@ class DeconvolutionFn(torch.autograd.Function):
         dx = dw = None
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, w.transpose(1, 2).contiguous())
+            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, w.transpose(1, 2).contiguous(), rules=down.fine.n)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
-            dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n)
+            dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n)
         return dx, dw, None
 
 
@@ -197,9 +247,11 @@ class BatchNormFn(torch.autograd.Function):
         save_mean = torch.empty(C, dtype=torch.float32, device=dev)
         save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
         scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        tok = _p0("bn_fwd", "bn", 12.0 * n * C, 0, 0.0, 0.0)
         check(lib.b200scn_bn_forward(ptr(x), ldx, n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
                                      ptr(save_mean), ptr(save_invstd), eps, momentum, 1 if train else 0, leak,
                                      ptr(y), C, ptr(scratch), _lib.stream_for(x)))
+        _p1(tok)
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
         ctx.leak = leak
         return y
@@ -215,9 +267,11 @@ class BatchNormFn(torch.autograd.Function):
         dweight = torch.empty(C, dtype=torch.float32, device=dev)
         dbias = torch.empty(C, dtype=torch.float32, device=dev)
         scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        tok = _p0("bn_bwd", "bn", 20.0 * n * C, 0, 0.0, 0.0)
         check(lib.b200scn_bn_backward(ptr(x), ldx, ptr(g), ldg, n, C, ptr(weight), ptr(bias), ptr(save_mean),
                                       ptr(save_invstd), ctx.leak, ptr(dx), C, ptr(dweight), ptr(dbias),
                                       ptr(scratch), _lib.stream_for(x)))
+        _p1(tok)
         return dx, dweight, dbias, None, None, None, None, None, None
 
 

@@ -7,20 +7,14 @@ from _util import copy_params, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _grad_report(a, b):
-    """(norm-wise rel err, median element-wise rel err).  ReLU masks make deep-net gradients discontinuous: one
-    mask flip (|pre-activation| below fp32 noise) anywhere changes the gradient norm-wise by ~1/sqrt(#elements)
-    ~ 2e-3 here, on EITHER side of the comparison, so the strict 1e-3 bound is asserted on the smooth variant of
-    the same net (leakiness 1) and per op (test_gpu_ops.py); for the ReLU net the median must be tight and the
-    norm-wise error small."""
-    a = a.detach().double().cpu()
-    b = b.detach().double().cpu()
-    scale = b.abs().mean() + 1e-30
-    med = float(((a - b).abs() / (b.abs() + scale)).median())
-    return rel_err(a, b), med
-
-
 def _run(kind, m, reps, res, scale, batch, npts, smooth):
+    """smooth=True: every BatchNorm(Leaky)ReLU made linear (leakiness 1) -> gradients are continuous and the
+    stated rel 1e-3 is asserted on logits, input gradient and every weight gradient.
+    smooth=False (the real ReLU net): a ReLU mask is discontinuous, so a pre-activation that sits within fp32
+    rounding of zero can land on different sides in two correct fp32 implementations; ONE such flip in a layer of
+    n x C elements moves the gradient norm-wise by ~1/sqrt(n*C) (1e-2 in a 120 x 96 layer) and that moves every
+    gradient upstream of it.  The test therefore counts the flips (forward hooks on every BatchNorm), checks each
+    is genuinely borderline, and widens the bound by 5/sqrt(n*C) per flip; with no flip the strict 1e-3 applies."""
     import sparseconvnet as scn
     from b200scn_synth import build_encoder, make_batch
     from oracle import scn_oracle as ref
@@ -28,19 +22,32 @@ def _run(kind, m, reps, res, scale, batch, npts, smooth):
     coords, feats, offs = make_batch(list(range(batch)), scale, n_points=npts)
     net_r = build_encoder(ref, kind, m, reps, res)
     net_g = build_encoder(scn, kind, m, reps, res)
-    if smooth:  # same nets with every BatchNorm(Leaky)ReLU made linear (leakiness 1): no mask discontinuities
+    if smooth:
         for net in (net_r, net_g):
             for mod in net.modules():
                 if hasattr(mod, "leakiness"):
                     mod.leakiness = 1.0
     copy_params(net_r, net_g)
     net_g.cuda()
+    bn_g, bn_r = [], []
+    for net, cls, store in ((net_g, scn.BatchNormalization, bn_g), (net_r, ref.BatchNormalization, bn_r)):
+        for mod in net.modules():
+            if isinstance(mod, cls):
+                mod.register_forward_hook(lambda _m, _i, out, store=store: store.append(out.features.detach().cpu()))
     fg = feats.clone().cuda().requires_grad_(True)
     fr = feats.clone().requires_grad_(True)
     og = net_g([coords, fg])
     o_r = net_r([coords, fr])
     assert og.shape == o_r.shape == (coords.shape[0], o_r.shape[1])
     assert rel_err(og, o_r) < 1e-3          # north_star: fp32 forward logits within rel 1e-3
+    slack = 0.0
+    if not smooth:
+        for yg, yr in zip(bn_g, bn_r):
+            mism = (yg > 0) != (yr > 0)
+            if mism.any():
+                rms = float(yr.pow(2).mean().sqrt())
+                assert float(torch.maximum(yg.abs(), yr.abs())[mism].max()) < 1e-4 * rms   # borderline only
+                slack += int(mism.sum()) * 5.0 / (yr.numel() ** 0.5)
     torch.manual_seed(1)
     go = torch.randn_like(o_r) / o_r.shape[0]
     og.backward(go.cuda())
@@ -48,11 +55,7 @@ def _run(kind, m, reps, res, scale, batch, npts, smooth):
     pairs = [("input", fg.grad, fr.grad)] + [(n, pg.grad, pr.grad) for (n, pg), (_, pr) in
                                              zip(net_g.named_parameters(), net_r.named_parameters())]
     for n, a, b in pairs:
-        norm, med = _grad_report(a, b)
-        if smooth:
-            assert norm < 1e-3, (n, norm)    # north_star: input and weight gradients within rel 1e-3
-        else:
-            assert med < 1e-4 and norm < 5e-2, (n, norm, med)
+        assert rel_err(a, b) < 1e-3 + slack, (n, rel_err(a, b), slack)   # north_star: gradients within rel 1e-3
     for (n, bg), (_, br) in zip(net_g.named_buffers(), net_r.named_buffers()):
         assert rel_err(bg, br) < 1e-4, n
 
