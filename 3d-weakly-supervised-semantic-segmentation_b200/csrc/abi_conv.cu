@@ -10,6 +10,9 @@ int scatter_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n
 int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
                  const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
                  float *dW, cudaStream_t st);
+bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int Cout, const float *W);
+int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
+                   int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st);
 }  // namespace b200scn
 
 using namespace b200scn;
@@ -24,7 +27,12 @@ int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t
   if (K < 1 || K > 64) return set_error("gather_conv: K=%d outside [1,64]", K);
   if (Cin < 1 || Cout < 1) return set_error("gather_conv: bad channel counts %d -> %d", Cin, Cout);
   if (n_out >= ((int64_t)1 << 31)) return set_error("gather_conv: too many rows");
-  (void)precision;
+  if (precision == 1) {
+    if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, W))
+      return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 256, 16-byte aligned rows "
+                       "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
+    return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+  }
   return gather_conv_simt(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
 }
 
@@ -49,6 +57,11 @@ int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, co
 }
 
 }  // extern "C"
+
+/* 1 if b200scn_gather_conv(precision = 1) accepts this shape */
+extern "C" int b200scn_gather_conv_tf32_ok(int Cin, int Cout, int64_t lda) {
+  return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 256 && (lda % 4 == 0);
+}
 
 extern "C" int b200scn_set_device(int device) {
   SCN_CUDA(cudaSetDevice(device));

@@ -71,33 +71,61 @@ def _c(t):
     return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
 
 
-def gather_conv(x, map_t, n_out, K, w, addend=None, rules=None):
-    """out[o] = sum_k x[map[o,k]] @ w[k] (+ addend[o]);  w (K,Cin,Cout).  `rules`: rule count (or Level) for accounting."""
+class GemmWeight:
+    """A per-offset weight stack for one GEMM direction: `w0` is the parameter (K,a,b); the GEMM multiplies rows by
+    w0[k] (transposed=False: Cin_g=a, Cout_g=b) or by w0[k]^T (transposed=True: Cin_g=b, Cout_g=a), optionally with
+    the offsets mirrored (flip: k -> K-1-k).  The fp32 kernels read (K,Cin_g,Cout_g), the tcgen05 kernels read the
+    K-major form (K,Cout_g,Cin_g); exactly one of the two is a free view of w0, the other is one small copy."""
+
+    def __init__(self, w0, transposed=False, flip=False):
+        self.w0, self.transposed, self.flip = w0, transposed, flip
+        self.cin, self.cout = (w0.shape[2], w0.shape[1]) if transposed else (w0.shape[1], w0.shape[2])
+        self.K = w0.shape[0]
+
+    def _base(self):
+        return self.w0.flip(0) if self.flip else self.w0
+
+    def rowmajor(self):   # (K,Cin_g,Cout_g)
+        w = self._base()
+        return (w.transpose(1, 2) if self.transposed else w).contiguous()
+
+    def kmajor(self):     # (K,Cout_g,Cin_g)
+        w = self._base()
+        return (w if self.transposed else w.transpose(1, 2)).contiguous()
+
+
+def _use_tf32(gw, lda):
+    return _precision[0] == 1 and lib.b200scn_gather_conv_tf32_ok(gw.cin, gw.cout, lda) == 1
+
+
+def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
+    """out[o] = sum_k x[map[o,k]] @ Wg[k] (+ addend[o]);  gw: GemmWeight.  `rules`: rule count (or Level) for accounting."""
     x, ldx = _c(x)
-    w = w.contiguous()
-    Cin, Cout = w.shape[1], w.shape[2]
+    Cin, Cout = gw.cin, gw.cout
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
     lda = 0
     if addend is not None:
         addend, lda = _c(addend)
+    tf32 = _use_tf32(gw, ldx)
+    w = gw.kmajor() if tf32 else gw.rowmajor()
     tok = _p0("gather%d" % K, "conv_gather", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out if rules is None else rules, 8.0 if map_t is not None else 0.0, 2.0 * Cin * Cout)
     check(lib.b200scn_gather_conv(ptr(x), ldx, ptr(map_t), n_out, K, ptr(w), Cin, Cout, ptr(addend), lda,
-                                  ptr(out), Cout, _precision[0], _lib.stream_for(x)))
+                                  ptr(out), Cout, 1 if tf32 else 0, _lib.stream_for(x)))
     _p1(tok)
     return out
 
 
-def scatter_conv(x, map_t, n_out, K, w):
-    """out[map[j,k]] = x[j] @ w[k]; every out row is addressed exactly once by a strided child map."""
+def scatter_conv(x, map_t, n_out, K, gw):
+    """out[map[j,k]] = x[j] @ Wg[k]; every out row is addressed exactly once by a strided child map."""
     x, ldx = _c(x)
-    w = w.contiguous()
-    Cin, Cout = w.shape[1], w.shape[2]
+    w = gw.rowmajor()
+    Cin, Cout = gw.cin, gw.cout
     out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
     tok = _p0("scatter%d" % K, "conv_scatter", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_scatter_conv(ptr(x), ldx, ptr(map_t), x.shape[0], K, ptr(w), Cin, Cout, ptr(out), Cout,
-                                   _precision[0], _lib.stream_for(x)))
+                                   0, _lib.stream_for(x)))
     _p1(tok)
     return out
 
@@ -125,7 +153,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
         nbr = level.subm_map()
         ctx.level = level
         ctx.save_for_backward(x, w)
-        return gather_conv(x, nbr, level.n, 27, w, rules=level)
+        return gather_conv(x, nbr, level.n, 27, GemmWeight(w), rules=level)
 
     @staticmethod
     def backward(ctx, g):
@@ -135,8 +163,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
-            wt = w.flip(0).transpose(1, 2).contiguous()
-            dx = gather_conv(g, level.subm_map(), level.n, 27, wt, rules=level)
+            dx = gather_conv(g, level.subm_map(), level.n, 27, GemmWeight(w, transposed=True, flip=True), rules=level)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = level.subm_pairs()
             dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
@@ -150,7 +177,7 @@ class ConvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return gather_conv(x, down.child_map(), down.coarse.n, down.K, w, rules=down.fine.n)
+        return gather_conv(x, down.child_map(), down.coarse.n, down.K, GemmWeight(w), rules=down.fine.n)
 
     @staticmethod
     def backward(ctx, g):
@@ -159,7 +186,7 @@ class ConvolutionFn(torch.autograd.Function):
         dx = dw = None
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, w.transpose(1, 2).contiguous())
+            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True))
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
             dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
@@ -174,7 +201,7 @@ class DeconvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return scatter_conv(x, down.child_map(), down.fine.n, down.K, w)
+        return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w))
 
     @staticmethod
     def backward(ctx, g):
@@ -183,7 +210,7 @@ class DeconvolutionFn(torch.autograd.Function):
         dx = dw = None
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, w.transpose(1, 2).contiguous(), rules=down.fine.n)
+            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, GemmWeight(w, transposed=True), rules=down.fine.n)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
             dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n)
@@ -220,7 +247,7 @@ class NetworkInNetworkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return gather_conv(x, None, x.shape[0], 1, w.unsqueeze(0))
+        return gather_conv(x, None, x.shape[0], 1, GemmWeight(w.unsqueeze(0)))
 
     @staticmethod
     def backward(ctx, g):
@@ -228,7 +255,7 @@ class NetworkInNetworkFn(torch.autograd.Function):
         dx = dw = None
         g = g.contiguous()
         if ctx.needs_input_grad[0]:
-            dx = gather_conv(g, None, g.shape[0], 1, w.t().contiguous().unsqueeze(0))
+            dx = gather_conv(g, None, g.shape[0], 1, GemmWeight(w.unsqueeze(0), transposed=True))
         if ctx.needs_input_grad[1]:
             dw = pair_dw(x, g, None, None, None, 1, x.shape[0])[0]
         return dx, dw

@@ -6,6 +6,15 @@ from _util import copy_params, random_cloud, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+TOL_TF32 = 2e-3   # TF32 operands (10-bit mantissa), fp32 accumulate: the stated tensor-core tolerance
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def precision(request):
+    import sparseconvnet as scn
+    scn.set_precision(request.param)
+    yield request.param
+    scn.set_precision("fp32")
 
 
 def _pair(coords, feats, nfeat):
@@ -20,7 +29,7 @@ def _pair(coords, feats, nfeat):
     return scn, ref, xg, xr, fg, fr
 
 
-def _check(mg, mr, xg, xr, fg, fr, dense_out=False):
+def _check(mg, mr, xg, xr, fg, fr, dense_out=False, TOL=TOL):
     copy_params(mr, mg)
     mg.cuda()
     yg, yr = mg(xg), mr(xr)
@@ -38,24 +47,26 @@ def _check(mg, mr, xg, xr, fg, fr, dense_out=False):
         assert rel_err(pg.grad, pr.grad) < TOL, n
 
 
-@pytest.mark.parametrize("cin,cout", [(3, 16), (16, 16), (32, 32), (48, 80), (64, 32), (5, 7)])
-def test_submanifold_conv(cin, cout):
+@pytest.mark.parametrize("cin,cout", [(3, 16), (16, 16), (32, 32), (48, 80), (64, 32), (5, 7), (224, 224), (128, 64), (64, 192)])
+def test_submanifold_conv(cin, cout, precision):
     coords, feats = random_cloud(cin * 100 + cout, 3000, 24, 2)
     scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
-    _check(scn.SubmanifoldConvolution(3, cin, cout, 3, False), ref.SubmanifoldConvolution(3, cin, cout, 3, False), xg, xr, fg, fr)
+    _check(scn.SubmanifoldConvolution(3, cin, cout, 3, False), ref.SubmanifoldConvolution(3, cin, cout, 3, False), xg, xr, fg, fr,
+           TOL=TOL if precision == "fp32" else TOL_TF32)
 
 
 @pytest.mark.parametrize("cin,cout,s", [(16, 32, 2), (32, 48, 2), (16, 24, 4), (6, 10, 2)])
-def test_strided_conv_deconv_unpool(cin, cout, s):
+def test_strided_conv_deconv_unpool(cin, cout, s, precision):
+    TOL = 1e-4 if precision == "fp32" else TOL_TF32
     coords, feats = random_cloud(cin + cout + s, 4000, 30, 2)
     scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
     mg = scn.Sequential(scn.Convolution(3, cin, cout, s, s, False), scn.Deconvolution(3, cout, cin, s, s, False))
     mr = ref.Sequential(ref.Convolution(3, cin, cout, s, s, False), ref.Deconvolution(3, cout, cin, s, s, False))
-    _check(mg, mr, xg, xr, fg, fr)
+    _check(mg, mr, xg, xr, fg, fr, TOL=TOL)
     scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
     mg = scn.Sequential(scn.Convolution(3, cin, cout, s, s, False), scn.UnPooling(3, s, s))
     mr = ref.Sequential(ref.Convolution(3, cin, cout, s, s, False), ref.UnPooling(3, s, s))
-    _check(mg, mr, xg, xr, fg, fr)
+    _check(mg, mr, xg, xr, fg, fr, TOL=TOL)
 
 
 @pytest.mark.parametrize("c,leak", [(16, 0.0), (32, 0.0), (112, 0.333), (448, 0.0), (6, 0.0)])
@@ -75,7 +86,7 @@ def test_batchnorm(c, leak):
 
 
 @pytest.mark.parametrize("a,b", [(64, 32), (32, 64), (7, 5)])
-def test_network_in_network_and_tables(a, b):
+def test_network_in_network_and_tables(a, b, precision):
     coords, feats = random_cloud(a + b, 3000, 24, 2)
     scn, ref, xg, xr, fg, fr = _pair(coords, feats, a)
 
@@ -86,7 +97,7 @@ def test_network_in_network_and_tables(a, b):
             ns.AddTable(),
             ns.ConcatTable().add(ns.Identity()).add(ns.NetworkInNetwork(b, a, False)),
             ns.JoinTable())
-    _check(net(scn), net(ref), xg, xr, fg, fr)
+    _check(net(scn), net(ref), xg, xr, fg, fr, TOL=TOL if precision == "fp32" else TOL_TF32)
 
 
 def test_output_layer_and_counters():
