@@ -13,6 +13,9 @@ int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const
 bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int Cout, const float *W);
 int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st);
+bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg);
+int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a, const int32_t *pair_g,
+               const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg, float *dW, cudaStream_t st);
 }  // namespace b200scn
 
 using namespace b200scn;
@@ -52,7 +55,8 @@ int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, co
                     int Ca, int Cg, float *dW, int precision, void *stream) {
   if (K < 1 || K > 64) return set_error("pair_dw: K=%d outside [1,64]", K);
   if (!offsets_dev && K != 1) return set_error("pair_dw: a single list requires K == 1");
-  (void)precision;
+  if (precision == 1 && pair_dw_tc_supported(A, lda, G, ldg, Ca, Cg))
+    return pair_dw_tc(A, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, Ca, Cg, dW, (cudaStream_t)stream);
   return pair_dw_simt(A, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, Ca, Cg, dW, (cudaStream_t)stream);
 }
 

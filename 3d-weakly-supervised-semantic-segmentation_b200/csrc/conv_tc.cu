@@ -81,7 +81,7 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
       if (kflag[k]) klist[n++] = k;
     *nk_p = n;
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(full + s, 128);
+      mbar_init(full + s, 32);
       mbar_init(empty + s, 1);
     }
     mbar_init(accum, 1);
@@ -97,31 +97,32 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   const int T = nk * nkb;
 
   if (warp < 4) {
-    // ------------------------------------------------------------ producers
-    const int c = tid & 7, r0 = tid >> 3;
-    for (int it = 0; it < T; ++it) {
+    // ------------------------------------------------------------ producers: warp w fills stages w, w+4, ...
+    // Every lane keeps 32 (+ Cout/4) 16-byte cp.async copies in flight, and the four warps work on four different
+    // stages at once, so one SM has tens of KB of gathers outstanding (the kernel is latency/L2-bound, not MMA-bound).
+    const int c = lane & 7, rl = lane >> 3;
+    // stage s is always filled by warp s (nstages <= 4): consecutive uses of a stage are ordered by that warp's
+    // program order, so the one-bit mbarrier phase parity can never alias
+    for (int it = warp; it < T && warp < nstages; it += nstages) {
       const int s = it % nstages;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(empty + s, ph ^ 1u);
       const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
       const int chan = kb * 32 + c * 4;
-      const bool cvalid = chan < Cin;
       const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = smap[(r0 + 16 * i) * K + k];
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx >= 0 && cvalid) v[i] = ldg_f4(A + (int64_t)idx * lda + chan);
+      if (chan < Cin) {
+        const float *acol = A + chan;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int r = rl + 4 * i;
+          const int idx = smap[r * K + k];
+          cp_async16(a_st + sw128(r, c), idx >= 0 ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
+                     idx >= 0 ? 16u : 0u);
+        }
+        const float *wk = Wkm + (int64_t)k * Cout * Cin + chan;
+        for (int n = rl; n < Cout; n += 4) cp_async16(b_st + sw128(n, c), wk + (int64_t)n * Cin, 16u);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sts_f4(a_st + sw128(r0 + 16 * i, c), v[i]);
-      const float *wk = Wkm + (int64_t)k * Cout * Cin + chan;
-      for (int n = r0; n < Cout; n += 16) {
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cvalid) w = ldg_f4(wk + (int64_t)n * Cin);
-        sts_f4(b_st + sw128(n, c), w);
-      }
+      cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(full + s);
     }
@@ -191,15 +192,10 @@ bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int C
 int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
   if (n_out <= 0) return 0;
-  // stage count: prefer two CTAs per SM (<= ~110 KB each), never below 2 stages
+  // four stages (one per producer warp); Cout <= 64 leaves room for two CTAs per SM
   int nstages = kMaxStages;
   TcSmemLayout L = tc_layout(Cout, K, nstages);
-  while (nstages > 3 && L.total > 112 * 1024) L = tc_layout(Cout, K, --nstages);
-  if (L.total > 112 * 1024) {
-    nstages = kMaxStages;
-    L = tc_layout(Cout, K, nstages);
-    while (nstages > 2 && L.total > 224 * 1024) L = tc_layout(Cout, K, --nstages);
-  }
+  while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(Cout, K, --nstages);
   if (L.total > 227 * 1024) return set_error("gather_conv_tc: shared memory %u too large", L.total);
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   dim3 grid((unsigned)ceil_div(n_out, kTcRows));
@@ -216,6 +212,180 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
   else SCN_LAUNCH_TC(256);
 #undef SCN_LAUNCH_TC
   SCN_CHECK_LAUNCH("gather_conv_tc");
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace b200scn
+
+// =====================================================================================================================
+// Weight gradient on the tensor cores:  dW[k] = sum over the pair list of offset k of  A[pa[p],:]^T (x) G[pg[p],:]
+// (replaces upstream's dConvolution_KMxKN_backward_dW atomicAdd kernels).
+//
+// The reduction dimension is the pair index, so both operands are "MN-major": a gathered feature row (128 bytes = 32
+// channels) IS one K-row of the shared-memory image (SWIZZLE_128B_BASE32B, the only tf32 MN-major layout).  One CTA reduces a
+// chunk of one offset's pair list into a Ca x Cg accumulator in TMEM (M = 128-channel tiles, N = Cg, K = 8 pairs per
+// tcgen05.mma), then adds it to dW[k] with fp32 reductions.  Same producer / MMA-issuer / epilogue roles as above.
+// =====================================================================================================================
+namespace b200scn {
+
+constexpr int kDwPairs = 32;  // pairs per stage (4 MMAs of K = 8)
+
+template <uint32_t NT>
+__global__ void __launch_bounds__(kTcThreads)
+pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ G, int64_t ldg,
+                  const int32_t *__restrict__ pair_a, const int32_t *__restrict__ pair_g,
+                  const int32_t *__restrict__ offsets, int n_single, int chunk, int Ca, int Cg, int nstages,
+                  uint32_t idesc, float *__restrict__ dW) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const int mt = (Ca + 127) >> 7;            // 128-channel M tiles
+  const int ab = (Ca + 31) >> 5;             // valid 32-channel blocks of A
+  const int gb = (Cg + 31) >> 5;
+  const uint32_t blk = kDwPairs * 128;       // one 32-channel block of one stage: 32 pair rows x 128 B
+  const uint32_t a_bytes = (uint32_t)(4 * mt) * blk, g_bytes = (uint32_t)gb * blk;
+  const uint32_t stage_bytes = a_bytes + g_bytes;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + (uint32_t)nstages * stage_bytes);
+  uint64_t *empty = full + kMaxStages;
+  uint64_t *accum = empty + kMaxStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k = blockIdx.y;
+  const int beg = offsets ? offsets[k] : 0;
+  const int end = offsets ? offsets[k + 1] : n_single;
+  const int p0 = beg + blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, end);
+  if (p0 >= p1) return;  // uniform for the whole CTA
+  const int T = (p1 - p0 + kDwPairs - 1) / kDwPairs;
+
+  if (tid == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(full + s, 32);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<NT>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    const int c = lane & 7, rl = lane >> 3;
+    for (int it = warp; it < T && warp < nstages; it += nstages) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(empty + s, ph ^ 1u);
+      const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
+      const int pbase = p0 + it * kDwPairs;
+#pragma unroll 2
+      for (int i = 0; i < kDwPairs / 4; ++i) {
+        const int r = rl + 4 * i;
+        const int p = pbase + r;
+        const bool live = p < p1;
+        const int ra = live ? (pair_a ? __ldg(pair_a + p) : p) : 0;
+        const int rg = live ? (pair_g ? __ldg(pair_g + p) : p) : 0;
+        const float *arow = A + (int64_t)ra * lda + c * 4;
+        const float *grow = G + (int64_t)rg * ldg + c * 4;
+        const uint32_t off = sw128_32b(r, c);
+        for (int b = 0; b < ab; ++b) {
+          const bool ok = live && (b * 32 + c * 4 < Ca);
+          cp_async16(a_st + (uint32_t)b * blk + off, ok ? (const void *)(arow + b * 32) : (const void *)A, ok ? 16u : 0u);
+        }
+        for (int b = 0; b < gb; ++b) {
+          const bool ok = live && (b * 32 + c * 4 < Cg);
+          cp_async16(g_st + (uint32_t)b * blk + off, ok ? (const void *)(grow + b * 32) : (const void *)G, ok ? 16u : 0u);
+        }
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(full + s);
+    }
+  } else if (lane == 0) {
+    for (int it = 0; it < T; ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
+      for (int t = 0; t < mt; ++t)
+        for (int j = 0; j < kDwPairs / 8; ++j) {
+          const uint64_t ad = make_smem_desc(a_st + (uint32_t)(4 * t) * blk + j * 1024, blk, 512, 1);
+          const uint64_t gd = make_smem_desc(g_st + j * 1024, blk, 512, 1);
+          mma_tf32(tmem + (uint32_t)(t * Cg), ad, gd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+        }
+      mma_commit(empty + s);
+    }
+    mma_commit(accum);
+  }
+
+  if (warp < 4) {
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    float *Wk = dW + (int64_t)k * Ca * Cg;
+    for (int t = 0; t < mt; ++t) {
+      const int ca = t * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < Cg; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * Cg + c0), v);
+        if (ca < Ca) {
+          float *o = Wk + (int64_t)ca * Cg + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(o + i, v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<NT>(tmem);
+}
+
+bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg) {
+  return (Ca % 4 == 0) && (Cg % 16 == 0) && Cg >= 16 && Cg <= 256 && Ca >= 4 && Ca <= 256 && (lda % 4 == 0) &&
+         (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
+         (((Ca + 127) >> 7) * Cg <= 512);
+}
+
+int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+               const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
+               float *dW, cudaStream_t st) {
+  SCN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * Ca * Cg, st));
+  if (n_pairs_max <= 0) return 0;
+  const int mt = (Ca + 127) >> 7, gb = (Cg + 31) >> 5;
+  const uint32_t stage_bytes = (uint32_t)(4 * mt + gb) * kDwPairs * 128;
+  int nstages = kMaxStages;
+  while (nstages > 2 && (uint32_t)nstages * stage_bytes + 256 + 1024 > 100 * 1024) --nstages;
+  const uint32_t smem = (uint32_t)nstages * stage_bytes + 256 + 1024;
+  if (smem > 227 * 1024) return set_error("pair_dw_tc: shared memory %u too large", smem);
+  // chunk of pairs per CTA: enough CTAs for ~4 per SM overall, a multiple of the stage size
+  int64_t want_chunks = ceil_div((int64_t)kNumSMs * 4, (int64_t)K);
+  int64_t chunk = ceil_div(n_pairs_max, want_chunks > 0 ? want_chunks : 1);
+  if (chunk < 512) chunk = 512;
+  if (chunk > 16384) chunk = 16384;
+  chunk = ceil_div(chunk, kDwPairs) * kDwPairs;
+  dim3 grid((unsigned)ceil_div(n_pairs_max, chunk), (unsigned)K);
+  const uint32_t idesc = make_idesc_tf32(128, Cg, 1, 1);
+  const int cols = mt * Cg;
+#define SCN_LAUNCH_DW(NT)                                                                                        \
+  do {                                                                                                           \
+    auto kern = pair_dw_tc_kernel<NT>;                                                                           \
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    kern<<<grid, kTcThreads, smem, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max,          \
+                                         (int)chunk, Ca, Cg, nstages, idesc, dW);                                \
+  } while (0)
+  if (cols <= 32) SCN_LAUNCH_DW(32);
+  else if (cols <= 64) SCN_LAUNCH_DW(64);
+  else if (cols <= 128) SCN_LAUNCH_DW(128);
+  else if (cols <= 256) SCN_LAUNCH_DW(256);
+  else SCN_LAUNCH_DW(512);
+#undef SCN_LAUNCH_DW
+  SCN_CHECK_LAUNCH("pair_dw_tc");
   count_launch(1);
   return 0;
 }

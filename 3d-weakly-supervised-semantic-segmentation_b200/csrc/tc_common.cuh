@@ -94,13 +94,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 //   K-major  operand (rows = M/N index, 128 B = 32 K-elements): SBO = bytes between 8-row groups, LBO ignored (=16 B)
 //   MN-major operand (rows = K index,   128 B = 32 MN-elements): LBO = bytes between 32-element MN blocks,
 //                                                               SBO = bytes between 8-row K groups
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//
+// tf32 MN-major operands only exist as SWIZZLE_128B_BASE32B (layout type 1): rows of 128 bytes = 32 MN-elements, one
+// row per K index, 32-byte chunk q of row r stored at chunk position q ^ (r & 3), 4-row K groups (SBO apart),
+// 32-element MN blocks LBO apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor, kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = MN-major operand, 0 = K-major.
@@ -116,8 +121,17 @@ __device__ __forceinline__ float4 ldg_f4(const float *p) { return __ldg(reinterp
 __device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 writes zeros (absent neighbour)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // swizzled byte offset of 16-byte chunk c in row r of a [rows x 128 B] SWIZZLE_128B image
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+// same for a SWIZZLE_128B_BASE32B image (32-byte swizzle granularity, 4-row period)
+__device__ __forceinline__ uint32_t sw128_32b(uint32_t r, uint32_t c) {
+  return r * 128u + ((((c >> 1) ^ (r & 3u)) << 5) | ((c & 1u) << 4));
+}
 
 }  // namespace tc
 }  // namespace b200scn

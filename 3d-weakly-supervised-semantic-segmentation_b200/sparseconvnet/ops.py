@@ -47,19 +47,30 @@ def profile_end():
     return out
 
 
+_event_pool = []
+
+
+def _event():
+    e = _event_pool.pop() if _event_pool else torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def profile_reserve(n):
+    """Pre-create n timing events so the timed region does not pay for cudaEventCreate."""
+    while len(_event_pool) < n:
+        _event_pool.append(torch.cuda.Event(enable_timing=True))
+
+
 def _p0(kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule):
     if _prof is None:
         return None
-    e0 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    return (kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule, e0)
+    return (kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule, _event())
 
 
 def _p1(tok):
     if tok is not None:
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record()
-        _prof.append(tok + (e1,))
+        _prof.append(tok + (_event(),))
 
 
 def _c(t):

@@ -37,39 +37,54 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, read in-process through NVML (the same counters as the
+    nvidia-smi clocks line in B200_PROFILING.md, without spawning a process that takes the driver lock every 200 ms)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
         self.t = threading.Thread(target=self._run, daemon=True)
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
 
     def _run(self):
+        nv = self.nv
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in o.strip().split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.rows.append((sm, rs))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def __enter__(self):
-        self.t.start()
+        if self.h is not None:
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop = True
-        self.t.join(timeout=6)
+        if self.h is not None:
+            self.t.join(timeout=2)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.h is None or not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        nv = self.nv
+        sm = sorted(r[0] for r in self.rows)
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = sorted(n for n, b in bits.items() if any(r[1] & b for r in self.rows))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm)}
 
 
 def _make_inputs(cfg, rank, n_distinct, n_points):
@@ -214,7 +229,9 @@ def run_b200(args):
         torch.cuda.synchronize()
         stats["voxels"] = 0
         launches0 = scn.launch_count()
-        scn_ops.profile_begin() if prof else None
+        if prof:
+            scn_ops.profile_reserve(800 * args.steps)
+            scn_ops.profile_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.steps):

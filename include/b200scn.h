@@ -96,7 +96,8 @@ int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_
 
 /* dW[k] = sum over pairs p of list k of A[pair_a[p],:]^T (x) G[pair_g[p],:]   (K,Ca,Cg) row-major.
  * pair_a / pair_g NULL => identity (row p).  offsets_dev NULL => one list [0,n_pairs_max).
- * n_pairs_max bounds the length of any single list.  dW is overwritten. */
+ * n_pairs_max bounds the length of any single list.  dW is overwritten.
+ * precision 1: TF32 tcgen05 tiles when the shape allows (Cg % 16 == 0, channels <= 256), else the fp32 kernel. */
 int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
                     const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max,
                     int Ca, int Cg, float *dW, int precision, void *stream);
