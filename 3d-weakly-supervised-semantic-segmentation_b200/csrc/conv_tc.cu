@@ -1,19 +1,22 @@
-// conv_tc.cu -- TF32 tensor-core gather convolution for sm_100a (tcgen05.mma, accumulators in TMEM).
+// conv_tc.cu -- TF32 tensor-core kernels for sm_100a (tcgen05.mma, accumulators in TMEM).
 //
-//   out[o,:] = sum_k A[map[o][k],:] . W[k]      (replaces upstream scn's
-//                                                 dConvolution_KMxKN_forward* fp32 FMA tiles)
+//   gather conv:  out[o,:] = sum_k A[map[o][k],:] . W[k]      (replaces upstream scn's
+//                                                               dConvolution_KMxKN_forward* fp32 FMA tiles)
 //
-// One CTA owns 128 output rows (one tcgen05 M=128 tile, N = Cout, accumulator = 128 lanes x Cout TMEM columns).
-// For every kernel offset k that is present in the tile and every 32-channel K block:
-//   warps 0-3 (producers)  gather the neighbour rows of A (16-byte loads, 8 lanes per 128-byte row, zeros for absent
-//                          neighbours) and the matching slice of W[k] into a SWIZZLE_128B shared-memory stage,
-//                          fence.proxy.async, arrive on the stage's "full" mbarrier;
-//   warp 4, one lane       waits "full", issues Cin_block/8 tcgen05.mma.kind::tf32 (K = 8 each), tcgen05.commit ->
-//                          the stage's "empty" mbarrier, so the producers run several stages ahead of the tensor pipe;
-//   epilogue (warps 0-3)   tcgen05.ld the accumulator (warp w owns TMEM lanes 32w..32w+31 = output rows), adds the
-//                          optional residual addend and writes every output row exactly once (no atomics, no
-//                          read-modify-write across offsets).
+// One CTA owns MSUB x 128 output rows (MSUB tcgen05 M=128 tiles sharing every weight stage, N = Cout, accumulators =
+// 128 lanes x MSUB*Cout TMEM columns).  For every kernel offset k present in the tile and every 32-channel K block:
+//   warps 0-3 (producers)  each warp owns one pipeline stage: it gathers the neighbour rows of A with 16-byte cp.async
+//                          (8 lanes per 128-byte row, zero-fill for absent neighbours) plus the matching slice of W[k]
+//                          into a SWIZZLE_128B shared-memory image, then fence.proxy.async + mbarrier arrive ("full");
+//   warp 4, one lane       waits "full", issues MSUB * Cin_block/8 tcgen05.mma.kind::tf32 (K = 8 each) and
+//                          tcgen05.commit -> the stage's "empty" mbarrier, so gathers run stages ahead of the tensor pipe;
+//   epilogue (warps 0-3)   tcgen05.ld the accumulators (warp w owns TMEM lanes 32w..32w+31 = output rows), adds the
+//                          optional residual addend and writes every output row exactly once.
+// Tiny levels (fewer tiles than SMs) additionally split the offsets over gridDim.y CTAs that reduce into a zeroed
+// output with fp32 atomics, because there the kernel is bound by the length of one CTA's dependent stage chain.
 // Weights arrive K-major: Wkm[k][n][c] (c contiguous), i.e. the B operand is read exactly as stored.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -21,7 +24,6 @@ namespace b200scn {
 
 using namespace tc;
 
-constexpr int kTcRows = 128;
 constexpr int kTcThreads = 160;
 constexpr int kMaxStages = 4;
 
@@ -29,29 +31,30 @@ struct TcSmemLayout {
   uint32_t a_bytes, b_bytes, stage_bytes, map_off, klist_off, bar_off, total;
 };
 
-static TcSmemLayout tc_layout(int Cout, int K, int nstages) {
+static TcSmemLayout tc_layout(int msub, int Cout, int K, int nstages) {
   TcSmemLayout L;
-  L.a_bytes = kTcRows * 128;
+  L.a_bytes = (uint32_t)msub * 128 * 128;
   L.b_bytes = (uint32_t)Cout * 128;
   L.stage_bytes = L.a_bytes + L.b_bytes;
   L.map_off = (uint32_t)nstages * L.stage_bytes;
-  L.klist_off = L.map_off + (uint32_t)kTcRows * K * 4;
+  L.klist_off = L.map_off + (uint32_t)msub * 128 * K * 4;
   L.bar_off = (L.klist_off + (uint32_t)(2 * K + 4) * 4 + 15) & ~15u;
   L.total = L.bar_off + (2 * kMaxStages + 1) * 8 + 16 + 1024;  // + alignment slack
   return L;
 }
 
-template <uint32_t NT>
+template <uint32_t NT, int MSUB>
 __global__ void __launch_bounds__(kTcThreads)
 gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *__restrict__ map, int n_rows, int K,
                       const float *__restrict__ Wkm, int Cin, int Cout, const float *__restrict__ addend,
                       int64_t ldadd, float *__restrict__ out, int64_t ldo, int nstages, uint32_t idesc,
                       uint32_t map_off, uint32_t klist_off, uint32_t bar_off) {
+  constexpr int ROWS = MSUB * 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
-  const uint32_t a_bytes = kTcRows * 128, b_bytes = (uint32_t)Cout * 128;
+  const uint32_t a_bytes = ROWS * 128, b_bytes = (uint32_t)Cout * 128;
   const uint32_t a_base = base, b_base = base + (uint32_t)nstages * a_bytes;
   int *smap = reinterpret_cast<int *>(sm + map_off);
   int *kflag = reinterpret_cast<int *>(sm + klist_off);
@@ -63,11 +66,12 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * kTcRows;
+  const int row0 = blockIdx.x * ROWS;
+  const int nsplit = gridDim.y, split = blockIdx.y;
 
   for (int k = tid; k < K; k += kTcThreads) kflag[k] = 0;
   __syncthreads();
-  for (int e = tid; e < kTcRows * K; e += kTcThreads) {
+  for (int e = tid; e < ROWS * K; e += kTcThreads) {
     int r = e / K, k = e - r * K;
     int v = -1;
     if (row0 + r < n_rows) v = map ? __ldg(map + (int64_t)(row0 + r) * K + k) : row0 + r;
@@ -79,7 +83,11 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
     int n = 0;
     for (int k = 0; k < K; ++k)
       if (kflag[k]) klist[n++] = k;
-    *nk_p = n;
+    // this CTA's share of the present offsets
+    const int per = (n + nsplit - 1) / nsplit;
+    const int lo = min(n, split * per), hi = min(n, lo + per);
+    for (int i = lo; i < hi; ++i) klist[i - lo] = klist[i];
+    *nk_p = hi - lo;
     for (int s = 0; s < nstages; ++s) {
       mbar_init(full + s, 32);
       mbar_init(empty + s, 1);
@@ -97,12 +105,11 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   const int T = nk * nkb;
 
   if (warp < 4) {
-    // ------------------------------------------------------------ producers: warp w fills stages w, w+4, ...
-    // Every lane keeps 32 (+ Cout/4) 16-byte cp.async copies in flight, and the four warps work on four different
-    // stages at once, so one SM has tens of KB of gathers outstanding (the kernel is latency/L2-bound, not MMA-bound).
-    const int c = lane & 7, rl = lane >> 3;
+    // ------------------------------------------------------------ producers
     // stage s is always filled by warp s (nstages <= 4): consecutive uses of a stage are ordered by that warp's
-    // program order, so the one-bit mbarrier phase parity can never alias
+    // program order, so the one-bit mbarrier phase parity can never alias.  Every lane keeps 32*MSUB (+ Cout/4)
+    // 16-byte copies in flight and the warps work on different stages at once.
+    const int c = lane & 7, rl = lane >> 3;
     for (int it = warp; it < T && warp < nstages; it += nstages) {
       const int s = it % nstages;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
@@ -113,7 +120,7 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
       if (chan < Cin) {
         const float *acol = A + chan;
 #pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < ROWS / 4; ++i) {
           const int r = rl + 4 * i;
           const int idx = smap[r * K + k];
           cp_async16(a_st + sw128(r, c), idx >= 0 ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
@@ -136,11 +143,13 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
       const int kb = it % nkb;
       const int kvalid = min(32, Cin - kb * 32);
       const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
-      for (int j = 0; j < (kvalid >> 3); ++j) {
-        const uint64_t ad = make_smem_desc(a_st + j * 32, 16, 1024);
-        const uint64_t bd = make_smem_desc(b_st + j * 32, 16, 1024);
-        mma_tf32(tmem, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
-      }
+#pragma unroll
+      for (int m = 0; m < MSUB; ++m)
+        for (int j = 0; j < (kvalid >> 3); ++j) {
+          const uint64_t ad = make_smem_desc(a_st + (uint32_t)m * (128 * 128) + j * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_st + j * 32, 16, 1024);
+          mma_tf32(tmem + (uint32_t)(m * Cout), ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+        }
       mma_commit(empty + s);
     }
     mma_commit(accum);
@@ -152,29 +161,38 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
       mbar_wait(accum, 0);
       tc_fence_after();
     }
-    const int row = row0 + warp * 32 + lane;
-    for (int c0 = 0; c0 < Cout; c0 += 16) {
-      float v[16];
-      if (T > 0) {
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      } else {
+    const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
-      }
-      if (row < n_rows) {
-        if (addend) {
-          const float *ad = addend + (int64_t)row * ldadd + c0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(ad + i);
-        }
-        float *o = out + (int64_t)row * ldo + c0;
-        if ((ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4 *>(o + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    for (int m = 0; m < MSUB; ++m) {
+      const int row = row0 + m * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < Cout; c0 += 16) {
+        float v[16];
+        if (T > 0) {
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * Cout + c0), v);
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = v[i];
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (row < n_rows) {
+          if (addend && split == 0) {
+            const float *ad = addend + (int64_t)row * ldadd + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(ad + i);
+          }
+          float *o = out + (int64_t)row * ldo + c0;
+          if (nsplit > 1) {
+            if (T > 0 || (addend && split == 0)) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) atomicAdd(o + i, v[i]);
+            }
+          } else if (vec) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4 *>(o + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = v[i];
+          }
         }
       }
     }
@@ -189,28 +207,58 @@ bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int C
          ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
 }
 
+template <uint32_t NT, int MSUB>
+static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const float *A, int64_t lda,
+                            const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin, int Cout,
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
+  auto kern = gather_conv_tc_kernel<NT, MSUB>;
+  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
+  kern<<<grid, kTcThreads, L.total, st>>>(A, lda, map, (int)n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, nstages,
+                                          idesc, L.map_off, L.klist_off, L.bar_off);
+  return 0;
+}
+
 int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
   if (n_out <= 0) return 0;
-  // four stages (one per producer warp); Cout <= 64 leaves room for two CTAs per SM
+  // 256-row CTAs (two accumulators share each weight stage) once there are enough rows to fill the chip twice over
+  // (Cout <= 64 fits two 128-row CTAs per SM, which hides gather latency better than sharing the weight stage)
+  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && Cout > 64 && 2 * Cout <= 512) ? 2 : 1;
+  if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
   int nstages = kMaxStages;
-  TcSmemLayout L = tc_layout(Cout, K, nstages);
-  while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(Cout, K, --nstages);
+  TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
+  while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(msub, Cout, K, --nstages);
   if (L.total > 227 * 1024) return set_error("gather_conv_tc: shared memory %u too large", L.total);
-  const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
-  dim3 grid((unsigned)ceil_div(n_out, kTcRows));
-#define SCN_LAUNCH_TC(NT)                                                                                         \
-  do {                                                                                                            \
-    auto kern = gather_conv_tc_kernel<NT>;                                                                        \
-    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));              \
-    kern<<<grid, kTcThreads, L.total, st>>>(A, lda, map, (int)n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo,  \
-                                            nstages, idesc, L.map_off, L.klist_off, L.bar_off);                   \
-  } while (0)
-  if (Cout <= 32) SCN_LAUNCH_TC(32);
-  else if (Cout <= 64) SCN_LAUNCH_TC(64);
-  else if (Cout <= 128) SCN_LAUNCH_TC(128);
-  else SCN_LAUNCH_TC(256);
-#undef SCN_LAUNCH_TC
+  const int64_t tiles = ceil_div(n_out, msub * 128);
+  // tiny levels: split the offsets over several CTAs per tile (atomic reduction into a zeroed output)
+  int nsplit = 1;
+  if (K > 1 && tiles * 2 <= kNumSMs) {
+    nsplit = (int)min((int64_t)K, (int64_t)kNumSMs / tiles);
+    if (nsplit > 9) nsplit = 9;
+  }
+  if (const char *e = getenv("B200SCN_TC_NSPLIT")) nsplit = max(1, min(K, atoi(e)));  // test hook
+  if (nsplit > 1) {
+    if (ldo == Cout) SCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_out * Cout, st));
+    else SCN_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * Cout, (size_t)n_out, st));
+  }
+  dim3 grid((unsigned)tiles, (unsigned)nsplit);
+  const int cols = msub * Cout;
+  int rc;
+#define SCN_ARGS grid, L, nstages, A, lda, map, n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, st
+  if (msub == 2) {
+    if (cols <= 64) rc = launch_gather_tc<64, 2>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tc<128, 2>(SCN_ARGS);
+    else if (cols <= 256) rc = launch_gather_tc<256, 2>(SCN_ARGS);
+    else rc = launch_gather_tc<512, 2>(SCN_ARGS);
+  } else {
+    if (cols <= 32) rc = launch_gather_tc<32, 1>(SCN_ARGS);
+    else if (cols <= 64) rc = launch_gather_tc<64, 1>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tc<128, 1>(SCN_ARGS);
+    else rc = launch_gather_tc<256, 1>(SCN_ARGS);
+  }
+#undef SCN_ARGS
+  if (rc) return rc;
   SCN_CHECK_LAUNCH("gather_conv_tc");
   count_launch(1);
   return 0;

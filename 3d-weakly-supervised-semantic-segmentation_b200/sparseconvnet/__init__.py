@@ -21,17 +21,28 @@ forward_pass_hidden_states = 0
 
 class _Module(types.ModuleType):
     """Module subclass so `scn.forward_pass_multiplyAdd_count` (train.py:50,86) stays a plain number for the
-    caller while rule counts are resolved lazily (they live on the device until somebody looks)."""
+    caller while rule counts are resolved lazily: they travel device -> pinned host asynchronously and are folded in
+    once their copy event has completed (never blocking a forward), or when somebody reads the counter.
+    Only the small pinned count buffers are kept, never the rulebooks themselves."""
+
+    def _fold(self, block):
+        pend = self.__dict__["_madd_pending"]
+        total = self.__dict__["_madd_base"]
+        while pend:
+            counts, event, mult = pend[0]
+            if event is not None:
+                if block:
+                    event.synchronize()
+                elif not event.query():
+                    break
+            total += int(counts.sum()) * mult if event is not None else int(counts) * mult
+            pend.pop(0)
+        self.__dict__["_madd_base"] = total
+        return total
 
     @property
     def forward_pass_multiplyAdd_count(self):
-        total = self.__dict__["_madd_base"]
-        for src, mult in self.__dict__["_madd_pending"]:
-            n = sum(src.rule_counts()) if hasattr(src, "rule_counts") else int(src)
-            total += n * mult
-        self.__dict__["_madd_base"] = total
-        self.__dict__["_madd_pending"] = []
-        return total
+        return self._fold(True)
 
     @forward_pass_multiplyAdd_count.setter
     def forward_pass_multiplyAdd_count(self, value):
@@ -40,9 +51,13 @@ class _Module(types.ModuleType):
 
     def _add_madds(self, src, mult):
         pend = self.__dict__["_madd_pending"]
-        pend.append((src, mult))
-        if len(pend) > 4096:  # nobody is reading the counter: fold what is already known
-            _ = self.forward_pass_multiplyAdd_count
+        if hasattr(src, "rule_counts"):
+            src.subm_map()
+            pend.append((src._counts_host, src._counts_event, mult))
+        else:
+            pend.append((int(src), None, mult))
+        if len(pend) > 64:
+            self._fold(False)
 
 
 _self = sys.modules[__name__]

@@ -89,3 +89,27 @@ def stream_for(t):
 def launch_count():
     """Kernels enqueued by the library since load (bench.py's gpu_launches)."""
     return int(lib.b200scn_launch_count())
+
+
+def round_rows(n):
+    """Row capacity for an n-row buffer: n rounded up so that only 4 significant bits survive (<= 12.5 % slack).
+    Site counts change a little every step (fresh augmentation); quantised capacities make every per-level buffer
+    size repeat exactly from step to step, so torch's caching allocator reuses blocks instead of fragmenting and
+    falling back to (synchronising) cudaMalloc."""
+    if n <= 4096:
+        return (n + 255) // 256 * 256 if n > 0 else 256
+    step = 1 << (n.bit_length() - 4)
+    return (n + step - 1) // step * step
+
+
+def alloc_rows(n, C, device, dtype=torch.float32, zero=False):
+    """(n, C) tensor that is a prefix view of a quantised-capacity buffer."""
+    cap = round_rows(n)
+    buf = (torch.zeros if zero else torch.empty)((cap, C), dtype=dtype, device=device)
+    return buf[:n]
+
+
+def alloc_flat(n, device, dtype, zero=False):
+    cap = round_rows(n)
+    buf = (torch.zeros if zero else torch.empty)(cap, dtype=dtype, device=device)
+    return buf[:n]

@@ -8,7 +8,7 @@ the host synchronises exactly once per forward (to learn the per-level site coun
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr
+from ._lib import alloc_flat, alloc_rows, check, lib, ptr
 
 # speculative pyramid built inside InputLayer before its single host sync: (stride, coarse levels)
 _pyramid_hint = [2, 6]
@@ -34,7 +34,7 @@ class Level:
     def subm_map(self):
         if self.nbr is None:
             dev = self.ukeys.device
-            self.nbr = torch.empty((self.n, 27), dtype=torch.int32, device=dev)
+            self.nbr = alloc_rows(self.n, 27, dev, torch.int32)
             self.nbr_counts = torch.zeros(27, dtype=torch.int32, device=dev)
             st = _lib.stream_for(self.ukeys)
             check(lib.b200scn_subm_map(ptr(self.ukeys), self.n, None, ptr(self.hkeys), ptr(self.hvals), self.cap,
@@ -66,9 +66,9 @@ def build_pairs(map_t, n, K, total):
     dev = map_t.device
     offsets = torch.empty(K + 1, dtype=torch.int32, device=dev)
     nbytes = lib.b200scn_pair_scratch_bytes(n, K)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    pair_in = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    pair_out = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    scratch = alloc_flat(nbytes, dev, torch.uint8)
+    pair_in = alloc_flat(max(total, 1), dev, torch.int32)
+    pair_out = alloc_flat(max(total, 1), dev, torch.int32)
     st = _lib.stream_for(map_t)
     check(lib.b200scn_pair_lists(ptr(map_t), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets), ptr(scratch), nbytes, st))
     return pair_in, pair_out, offsets
@@ -85,7 +85,7 @@ class Down:
     def child_map(self):
         if self.child is None:
             dev = self.parent.device
-            self.child = torch.empty((self.coarse.n, self.K), dtype=torch.int32, device=dev)
+            self.child = alloc_rows(self.coarse.n, self.K, dev, torch.int32)
             st = _lib.stream_for(self.parent)
             check(lib.b200scn_child_map(ptr(self.parent), ptr(self.off), self.fine.n, None, self.K,
                                         ptr(self.child), self.coarse.n, st))
@@ -115,10 +115,11 @@ class Metadata:
             raise ValueError("InputLayer: coords must be (N,3) or (N,4), got %s" % (tuple(coords.shape),))
         coords = coords.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
         P = coords.shape[0]
+        Pc = _lib.round_rows(max(P, 1))   # quantised capacity of every per-point / per-site buffer
         self.P, self.mode = P, mode
         st = _lib.stream_for(coords)
         i32, i64 = torch.int32, torch.int64
-        keys = torch.empty(max(P, 1), dtype=i64, device=device)
+        keys = torch.empty(Pc, dtype=i64, device=device)
         s_hint, depth = _pyramid_hint
         sizes = [int(spatial_size)]
         while len(sizes) <= depth and sizes[-1] % s_hint == 0 and sizes[-1] // s_hint >= 1 and sizes[-1] > 1:
@@ -127,15 +128,15 @@ class Metadata:
         # header: [err, n_0, n_1, ..., n_{nlev-1}]
         hdr = torch.zeros(1 + nlev, dtype=i32, device=device)
         check(lib.b200scn_pack_coords(ptr(coords), P, coords.shape[1], int(spatial_size), ptr(keys), ptr(hdr), st))
-        cap = lib.b200scn_hash_capacity(P)
-        sbytes = lib.b200scn_grid_scratch_bytes(P)
+        cap = lib.b200scn_hash_capacity(Pc)
+        sbytes = lib.b200scn_grid_scratch_bytes(Pc)
         scratch = torch.empty(sbytes, dtype=torch.uint8, device=device)
-        self.pv = torch.empty(max(P, 1), dtype=i32, device=device)
-        self.first_row = torch.empty(max(P, 1), dtype=i32, device=device)
-        self.last_row = torch.empty(max(P, 1), dtype=i32, device=device)
-        self.count = torch.empty(max(P, 1), dtype=i32, device=device)
+        self.pv = torch.empty(Pc, dtype=i32, device=device)
+        self.first_row = torch.empty(Pc, dtype=i32, device=device)
+        self.last_row = torch.empty(Pc, dtype=i32, device=device)
+        self.count = torch.empty(Pc, dtype=i32, device=device)
         raw = []
-        ukeys = torch.empty(max(P, 1), dtype=i64, device=device)
+        ukeys = torch.empty(Pc, dtype=i64, device=device)
         hkeys = torch.empty(cap, dtype=i64, device=device)
         hvals = torch.empty(cap, dtype=i32, device=device)
         check(lib.b200scn_grid_build(ptr(keys), P, None, ptr(hkeys), ptr(hvals), cap, ptr(self.pv), ptr(ukeys),
@@ -145,11 +146,11 @@ class Metadata:
         for li in range(1, nlev):
             fu = raw[-1][0]
             ckeys = keys  # reuse: the packed point keys are dead after the level-0 build
-            off = torch.empty(max(P, 1), dtype=torch.uint8, device=device)
-            parent = torch.empty(max(P, 1), dtype=i32, device=device)
+            off = torch.empty(Pc, dtype=torch.uint8, device=device)
+            parent = torch.empty(Pc, dtype=i32, device=device)
             n_dev = hdr[li:].data_ptr()
             check(lib.b200scn_coarse_keys(ptr(fu), P, n_dev, s_hint, ptr(ckeys), ptr(off), st))
-            cu = torch.empty(max(P, 1), dtype=i64, device=device)
+            cu = torch.empty(Pc, dtype=i64, device=device)
             ck = torch.empty(cap, dtype=i64, device=device)
             cv = torch.empty(cap, dtype=i32, device=device)
             check(lib.b200scn_grid_build(ptr(ckeys), P, n_dev, ptr(ck), ptr(cv), cap, ptr(parent), ptr(cu),

@@ -6,7 +6,7 @@ reaches it.  All tensors are CUDA fp32; there is no CPU path.
 import torch
 
 from . import _lib
-from ._lib import check, lib, ptr
+from ._lib import alloc_rows, check, lib, ptr
 
 # 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05) where the kernel supports the shape
 _precision = [0]
@@ -38,12 +38,17 @@ def profile_end():
     torch.cuda.synchronize()
     out = {}
     for kind, kernel, nrows_bytes, rules, per_rule_bytes, flops_per_rule, e0, e1 in recs:
-        r = sum(rules.rule_counts()) if hasattr(rules, "rule_counts") else int(rules)
+        r = int(rules[1].sum()) if isinstance(rules, tuple) else int(rules)
         d = out.setdefault(kind, {"ms": 0.0, "n": 0, "bytes": 0.0, "flops": 0.0, "kernel": kernel})
         d["ms"] += e0.elapsed_time(e1)
         d["n"] += 1
         d["bytes"] += nrows_bytes + per_rule_bytes * r
         d["flops"] += flops_per_rule * r
+        sh = d.setdefault("shapes", {}).setdefault("%dx%d r%d" % (int(flops_per_rule), int(nrows_bytes), r), [0.0, 0, 0.0, 0.0])
+        sh[0] += e0.elapsed_time(e1)
+        sh[1] += 1
+        sh[2] += nrows_bytes + per_rule_bytes * r
+        sh[3] += flops_per_rule * r
     return out
 
 
@@ -65,6 +70,9 @@ def profile_reserve(n):
 def _p0(kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule):
     if _prof is None:
         return None
+    if hasattr(rules, "rule_counts"):   # keep only the (pinned, asynchronously filled) counts, not the Level
+        rules.subm_map()
+        rules = ("counts", rules._counts_host)
     return (kind, kernel, fixed_bytes, rules, per_rule_bytes, flops_per_rule, _event())
 
 
@@ -105,19 +113,19 @@ class GemmWeight:
         return (w if self.transposed else w.transpose(1, 2)).contiguous()
 
 
-def _use_tf32(gw, lda):
-    return _precision[0] == 1 and lib.b200scn_gather_conv_tf32_ok(gw.cin, gw.cout, lda) == 1
+def _use_tf32(gw, lda, x):
+    return _precision[0] == 1 and x.data_ptr() % 16 == 0 and lib.b200scn_gather_conv_tf32_ok(gw.cin, gw.cout, lda) == 1
 
 
 def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
     """out[o] = sum_k x[map[o,k]] @ Wg[k] (+ addend[o]);  gw: GemmWeight.  `rules`: rule count (or Level) for accounting."""
     x, ldx = _c(x)
     Cin, Cout = gw.cin, gw.cout
-    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    out = alloc_rows(n_out, Cout, x.device)
     lda = 0
     if addend is not None:
         addend, lda = _c(addend)
-    tf32 = _use_tf32(gw, ldx)
+    tf32 = _use_tf32(gw, ldx, x)
     w = gw.kmajor() if tf32 else gw.rowmajor()
     tok = _p0("gather%d" % K, "conv_gather", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out if rules is None else rules, 8.0 if map_t is not None else 0.0, 2.0 * Cin * Cout)
@@ -132,7 +140,7 @@ def scatter_conv(x, map_t, n_out, K, gw):
     x, ldx = _c(x)
     w = gw.rowmajor()
     Cin, Cout = gw.cin, gw.cout
-    out = torch.empty((n_out, Cout), dtype=torch.float32, device=x.device)
+    out = alloc_rows(n_out, Cout, x.device)
     tok = _p0("scatter%d" % K, "conv_scatter", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_scatter_conv(ptr(x), ldx, ptr(map_t), x.shape[0], K, ptr(w), Cin, Cout, ptr(out), Cout,
@@ -171,7 +179,6 @@ class SubmanifoldConvFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         level = ctx.level
         dx = dw = None
-        g = g.contiguous()
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
             dx = gather_conv(g, level.subm_map(), level.n, 27, GemmWeight(w, transposed=True, flip=True), rules=level)
@@ -195,7 +202,6 @@ class ConvolutionFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         down = ctx.down
         dx = dw = None
-        g = g.contiguous()
         if ctx.needs_input_grad[0]:
             dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True))
         if ctx.needs_input_grad[1]:
@@ -219,7 +225,6 @@ class DeconvolutionFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         down = ctx.down
         dx = dw = None
-        g = g.contiguous()
         if ctx.needs_input_grad[0]:
             dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, GemmWeight(w, transposed=True), rules=down.fine.n)
         if ctx.needs_input_grad[1]:
@@ -236,7 +241,7 @@ class UnPoolingFn(torch.autograd.Function):
         ctx.down = down
         x, ldx = _c(x)
         C = x.shape[1]
-        out = torch.empty((down.fine.n, C), dtype=torch.float32, device=x.device)
+        out = alloc_rows(down.fine.n, C, x.device)
         check(lib.b200scn_unpool(ptr(x), ldx, ptr(down.parent), down.fine.n, C, ptr(out), C, _lib.stream_for(x)))
         return out
 
@@ -245,7 +250,7 @@ class UnPoolingFn(torch.autograd.Function):
         down = ctx.down
         g, ldg = _c(g)
         C = g.shape[1]
-        dx = torch.empty((down.coarse.n, C), dtype=torch.float32, device=g.device)
+        dx = alloc_rows(down.coarse.n, C, g.device)
         check(lib.b200scn_unpool_bwd(ptr(g), ldg, ptr(down.child_map()), down.coarse.n, down.K, C, ptr(dx), C,
                                      _lib.stream_for(g)))
         return dx, None
@@ -264,7 +269,6 @@ class NetworkInNetworkFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         dx = dw = None
-        g = g.contiguous()
         if ctx.needs_input_grad[0]:
             dx = gather_conv(g, None, g.shape[0], 1, GemmWeight(w.unsqueeze(0), transposed=True))
         if ctx.needs_input_grad[1]:
@@ -281,7 +285,7 @@ class BatchNormFn(torch.autograd.Function):
         x, ldx = _c(x)
         n, C = x.shape
         dev = x.device
-        y = torch.empty((n, C), dtype=torch.float32, device=dev)
+        y = alloc_rows(n, C, dev)
         save_mean = torch.empty(C, dtype=torch.float32, device=dev)
         save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
         scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
@@ -301,7 +305,7 @@ class BatchNormFn(torch.autograd.Function):
         g, ldg = _c(g)
         n, C = x.shape
         dev = x.device
-        dx = torch.empty((n, C), dtype=torch.float32, device=dev)
+        dx = alloc_rows(n, C, dev)
         dweight = torch.empty(C, dtype=torch.float32, device=dev)
         dbias = torch.empty(C, dtype=torch.float32, device=dev)
         scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
@@ -322,7 +326,7 @@ class InputFeaturesFn(torch.autograd.Function):
         if feats.dtype != torch.float32:
             raise TypeError("InputLayer: features must be float32, got %s" % feats.dtype)
         P, C = feats.shape
-        out = torch.zeros((n0, C), dtype=torch.float32, device=feats.device)
+        out = alloc_rows(n0, C, feats.device, zero=True)
         check(lib.b200scn_input_features(ptr(feats), P, C, ptr(md.pv), ptr(md.count), ptr(md.first_row),
                                          ptr(md.last_row), md.mode, ptr(out), _lib.stream_for(feats)))
         ctx.md = md
@@ -333,7 +337,7 @@ class InputFeaturesFn(torch.autograd.Function):
         md = ctx.md
         g = g.contiguous()
         C = g.shape[1]
-        d = torch.empty((md.P, C), dtype=torch.float32, device=g.device)
+        d = alloc_rows(md.P, C, g.device)
         check(lib.b200scn_input_features_bwd(ptr(g), md.P, C, ptr(md.pv), ptr(md.count), ptr(md.first_row),
                                              ptr(md.last_row), md.mode, ptr(d), _lib.stream_for(g)))
         return d, None, None
@@ -346,7 +350,7 @@ class OutputFeaturesFn(torch.autograd.Function):
     def forward(ctx, feats, md):
         feats, ldf = _c(feats)
         C = feats.shape[1]
-        out = torch.empty((md.P, C), dtype=torch.float32, device=feats.device)
+        out = alloc_rows(md.P, C, feats.device)
         check(lib.b200scn_output_features(ptr(feats), ldf, md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
                                           md.mode, ptr(out), _lib.stream_for(feats)))
         ctx.md, ctx.n = md, feats.shape[0]
@@ -357,7 +361,7 @@ class OutputFeaturesFn(torch.autograd.Function):
         md = ctx.md
         g = g.contiguous()
         C = g.shape[1]
-        d = torch.zeros((ctx.n, C), dtype=torch.float32, device=g.device)
+        d = alloc_rows(ctx.n, C, g.device, zero=True)
         check(lib.b200scn_output_features_bwd(ptr(g), md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
                                               md.mode, ptr(d), C, _lib.stream_for(g)))
         return d, None

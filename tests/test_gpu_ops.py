@@ -9,11 +9,21 @@ TOL = 1e-4
 TOL_TF32 = 2e-3   # TF32 operands (10-bit mantissa), fp32 accumulate: the stated tensor-core tolerance
 
 
-@pytest.fixture(params=["fp32", "tf32"])
+@pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3"])
 def precision(request):
+    """fp32 CUDA-core path, TF32 tcgen05 path, and the TF32 path with its large-level (256-row CTAs) and tiny-level
+    (offsets split over CTAs) variants forced on, which the heuristics would not pick at test sizes."""
+    import os
     import sparseconvnet as scn
-    scn.set_precision(request.param)
-    yield request.param
+    name = request.param
+    scn.set_precision("fp32" if name == "fp32" else "tf32")
+    if name == "tf32-msub2":
+        os.environ["B200SCN_TC_MSUB"] = "2"
+    if name == "tf32-split3":
+        os.environ["B200SCN_TC_NSPLIT"] = "3"
+    yield "fp32" if name == "fp32" else "tf32"
+    os.environ.pop("B200SCN_TC_MSUB", None)
+    os.environ.pop("B200SCN_TC_NSPLIT", None)
     scn.set_precision("fp32")
 
 
