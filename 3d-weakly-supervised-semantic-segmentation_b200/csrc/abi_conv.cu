@@ -1,4 +1,6 @@
 // abi_conv.cu -- C-ABI dispatch for the convolution entry points (fp32 CUDA-core vs TF32 tcgen05 paths).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200scn {
@@ -13,6 +15,9 @@ int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const
 bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int Cout, const float *W);
 int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st);
+int gather_conv_tma(const float *A, int64_t lda, int64_t n_in, const int32_t *map, int64_t n_out, int K,
+                    const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
+                    cudaStream_t st);
 bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg);
 int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a, const int32_t *pair_g,
                const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg, float *dW, cudaStream_t st);
@@ -22,7 +27,7 @@ using namespace b200scn;
 
 extern "C" {
 
-int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K,
+int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t *map, int64_t n_out, int K,
                         const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
                         float *out, int64_t ldo, int precision, void *stream) {
   if (n_out <= 0) return 0;
@@ -34,7 +39,10 @@ int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t
     if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, W))
       return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 256, 16-byte aligned rows "
                        "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
-    return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+    const char *e = getenv("B200SCN_TC_TMA");   // 0 selects the cp.async producer variant
+    if (e && atoi(e) == 0)
+      return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+    return gather_conv_tma(A, lda, n_in, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
   }
   return gather_conv_simt(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
 }

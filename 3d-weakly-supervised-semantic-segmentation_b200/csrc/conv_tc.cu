@@ -43,13 +43,16 @@ static TcSmemLayout tc_layout(int msub, int Cout, int K, int nstages) {
   return L;
 }
 
-template <uint32_t NT, int MSUB>
-__global__ void __launch_bounds__(kTcThreads)
+// NPW producer warps (4: one per stage; 8: two per stage, each gathering half of the stage's rows and weights).
+template <uint32_t NT, int MSUB, int NPW>
+__global__ void __launch_bounds__(32 * (NPW + 1))
 gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *__restrict__ map, int n_rows, int K,
                       const float *__restrict__ Wkm, int Cin, int Cout, const float *__restrict__ addend,
                       int64_t ldadd, float *__restrict__ out, int64_t ldo, int nstages, uint32_t idesc,
                       uint32_t map_off, uint32_t klist_off, uint32_t bar_off) {
   constexpr int ROWS = MSUB * 128;
+  constexpr int NTHREADS = 32 * (NPW + 1);
+  constexpr int WPS = NPW / 4;  // producer warps per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -69,9 +72,9 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   const int row0 = blockIdx.x * ROWS;
   const int nsplit = gridDim.y, split = blockIdx.y;
 
-  for (int k = tid; k < K; k += kTcThreads) kflag[k] = 0;
+  for (int k = tid; k < K; k += NTHREADS) kflag[k] = 0;
   __syncthreads();
-  for (int e = tid; e < ROWS * K; e += kTcThreads) {
+  for (int e = tid; e < ROWS * K; e += NTHREADS) {
     int r = e / K, k = e - r * K;
     int v = -1;
     if (row0 + r < n_rows) v = map ? __ldg(map + (int64_t)(row0 + r) * K + k) : row0 + r;
@@ -89,13 +92,13 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
     for (int i = lo; i < hi; ++i) klist[i - lo] = klist[i];
     *nk_p = hi - lo;
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(full + s, 32);
+      mbar_init(full + s, 32 * WPS);
       mbar_init(empty + s, 1);
     }
     mbar_init(accum, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<NT>(tmem_slot);
+  if (warp == NPW) tmem_alloc<NT>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -104,34 +107,39 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   const int nkb = (Cin + 31) >> 5;
   const int T = nk * nkb;
 
-  if (warp < 4) {
+  if (warp < NPW) {
     // ------------------------------------------------------------ producers
-    // stage s is always filled by warp s (nstages <= 4): consecutive uses of a stage are ordered by that warp's
-    // program order, so the one-bit mbarrier phase parity can never alias.  Every lane keeps 32*MSUB (+ Cout/4)
-    // 16-byte copies in flight and the warps work on different stages at once.
+    // stage s is always filled by the same warp(s) (s, and s + nstages when WPS == 2): consecutive uses of a stage
+    // are ordered by that warp's program order, so the one-bit mbarrier phase parity can never alias.  Every lane
+    // keeps ROWS/(4*WPS) (+ Cout/(4*WPS)) 16-byte copies in flight and the warps work on different stages at once.
     const int c = lane & 7, rl = lane >> 3;
-    for (int it = warp; it < T && warp < nstages; it += nstages) {
-      const int s = it % nstages;
-      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
-      mbar_wait(empty + s, ph ^ 1u);
-      const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
-      const int chan = kb * 32 + c * 4;
-      const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
-      if (chan < Cin) {
-        const float *acol = A + chan;
+    const int my_stage = warp % nstages, half = warp / nstages;
+    if (half < WPS) {
+      constexpr int RPW = ROWS / WPS;  // rows per producer warp
+      const int rbase = half * RPW;
+      for (int it = my_stage; it < T; it += nstages) {
+        const int s = my_stage;
+        const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
+        const int chan = kb * 32 + c * 4;
+        const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
+        if (chan < Cin) {
+          const float *acol = A + chan;
 #pragma unroll 8
-        for (int i = 0; i < ROWS / 4; ++i) {
-          const int r = rl + 4 * i;
-          const int idx = smap[r * K + k];
-          cp_async16(a_st + sw128(r, c), idx >= 0 ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
-                     idx >= 0 ? 16u : 0u);
+          for (int i = 0; i < RPW / 4; ++i) {
+            const int r = rbase + rl + 4 * i;
+            const int idx = smap[r * K + k];
+            cp_async16(a_st + sw128(r, c), idx >= 0 ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
+                       idx >= 0 ? 16u : 0u);
+          }
+          const float *wk = Wkm + (int64_t)k * Cout * Cin + chan;
+          for (int n = rl + 4 * half; n < Cout; n += 4 * WPS) cp_async16(b_st + sw128(n, c), wk + (int64_t)n * Cin, 16u);
         }
-        const float *wk = Wkm + (int64_t)k * Cout * Cin + chan;
-        for (int n = rl; n < Cout; n += 4) cp_async16(b_st + sw128(n, c), wk + (int64_t)n * Cin, 16u);
+        cp_async_wait_all();
+        fence_proxy_async();
+        mbar_arrive(full + s);
       }
-      cp_async_wait_all();
-      fence_proxy_async();
-      mbar_arrive(full + s);
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------ MMA issuer (one thread)
@@ -155,20 +163,21 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
     mma_commit(accum);
   }
 
-  if (warp < 4) {
+  if (warp < NPW) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    // warp w may only read TMEM lanes 32*(w%4)..+31; with 8 producer warps, warps 4-7 take the second sub-tile
     if (T > 0) {
       mbar_wait(accum, 0);
       tc_fence_after();
     }
     const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-#pragma unroll
-    for (int m = 0; m < MSUB; ++m) {
-      const int row = row0 + m * 128 + warp * 32 + lane;
+    const int q = warp & 3;
+    for (int m = warp >> 2; m < MSUB; m += NPW / 4) {
+      const int row = row0 + m * 128 + q * 32 + lane;
       for (int c0 = 0; c0 < Cout; c0 += 16) {
         float v[16];
         if (T > 0) {
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * Cout + c0), v);
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * Cout + c0), v);
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -199,7 +208,7 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<NT>(tmem);
+  if (warp == NPW) tmem_dealloc<NT>(tmem);
 }
 
 bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int Cout, const float *W) {
@@ -207,14 +216,14 @@ bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int C
          ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
 }
 
-template <uint32_t NT, int MSUB>
+template <uint32_t NT, int MSUB, int NPW>
 static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const float *A, int64_t lda,
                             const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin, int Cout,
                             const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
-  auto kern = gather_conv_tc_kernel<NT, MSUB>;
+  auto kern = gather_conv_tc_kernel<NT, MSUB, NPW>;
   SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
-  kern<<<grid, kTcThreads, L.total, st>>>(A, lda, map, (int)n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, nstages,
+  kern<<<grid, 32 * (NPW + 1), L.total, st>>>(A, lda, map, (int)n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, nstages,
                                           idesc, L.map_off, L.klist_off, L.bar_off);
   return 0;
 }
@@ -223,8 +232,8 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
   if (n_out <= 0) return 0;
   // 256-row CTAs (two accumulators share each weight stage) once there are enough rows to fill the chip twice over
-  // (Cout <= 64 fits two 128-row CTAs per SM, which hides gather latency better than sharing the weight stage)
-  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && Cout > 64 && 2 * Cout <= 512) ? 2 : 1;
+  // (eight producer warps then gather for one CTA per SM; the weight slice of every stage is fetched once per 256 rows)
+  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && 2 * Cout <= 512) ? 2 : 1;
   if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
   int nstages = kMaxStages;
   TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
@@ -247,15 +256,15 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
   int rc;
 #define SCN_ARGS grid, L, nstages, A, lda, map, n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, st
   if (msub == 2) {
-    if (cols <= 64) rc = launch_gather_tc<64, 2>(SCN_ARGS);
-    else if (cols <= 128) rc = launch_gather_tc<128, 2>(SCN_ARGS);
-    else if (cols <= 256) rc = launch_gather_tc<256, 2>(SCN_ARGS);
-    else rc = launch_gather_tc<512, 2>(SCN_ARGS);
+    if (cols <= 64) rc = launch_gather_tc<64, 2, 8>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tc<128, 2, 8>(SCN_ARGS);
+    else if (cols <= 256) rc = launch_gather_tc<256, 2, 8>(SCN_ARGS);
+    else rc = launch_gather_tc<512, 2, 8>(SCN_ARGS);
   } else {
-    if (cols <= 32) rc = launch_gather_tc<32, 1>(SCN_ARGS);
-    else if (cols <= 64) rc = launch_gather_tc<64, 1>(SCN_ARGS);
-    else if (cols <= 128) rc = launch_gather_tc<128, 1>(SCN_ARGS);
-    else rc = launch_gather_tc<256, 1>(SCN_ARGS);
+    if (cols <= 32) rc = launch_gather_tc<32, 1, 4>(SCN_ARGS);
+    else if (cols <= 64) rc = launch_gather_tc<64, 1, 4>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tc<128, 1, 4>(SCN_ARGS);
+    else rc = launch_gather_tc<256, 1, 4>(SCN_ARGS);
   }
 #undef SCN_ARGS
   if (rc) return rc;
@@ -434,6 +443,266 @@ int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const i
   else SCN_LAUNCH_DW(512);
 #undef SCN_LAUNCH_DW
   SCN_CHECK_LAUNCH("pair_dw_tc");
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace b200scn
+
+// =====================================================================================================================
+// TMA variant of the gather convolution (the default): the per-lane cp.async producers are replaced by ONE warp that
+// issues tile::gather4 TMA copies -- each lane names four neighbour rows (absent neighbour = an out-of-range row index,
+// which the TMA unit zero-fills), so one warp instruction stages 128 gathered rows x 128 bytes, already in the
+// SWIZZLE_128B image tcgen05.mma reads -- plus one tiled TMA load for the weight slice.  Completion is counted in bytes
+// on the stage's mbarrier (no LSU traffic, no proxy fence), so the producer runs `nstages` stages ahead of the tensor
+// pipe.  Warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer.
+// =====================================================================================================================
+namespace b200scn {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: rows x cols (cols contiguous, row pitch ld floats), box = box_rows x 32 floats, 128-byte swizzle
+static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %d ld %lld box %d", (int)r,
+                                          (long long)rows, cols, (long long)ld, box_rows);
+  return 0;
+}
+
+constexpr int kTmaThreads = 192;
+
+template <uint32_t NT, int MSUB>
+__global__ void __launch_bounds__(kTmaThreads)
+gather_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const int32_t *__restrict__ map, int n_rows, int n_in, int K, int Cin, int Cout,
+                       const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out, int64_t ldo,
+                       int nstages, uint32_t idesc, uint32_t map_off, uint32_t klist_off, uint32_t bar_off) {
+  constexpr int ROWS = MSUB * 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t a_bytes = ROWS * 128, b_bytes = (uint32_t)Cout * 128;
+  const uint32_t a_base = base, b_base = base + (uint32_t)nstages * a_bytes;
+  int *smap = reinterpret_cast<int *>(sm + map_off);
+  int *kflag = reinterpret_cast<int *>(sm + klist_off);
+  int *klist = kflag + K;
+  int *nk_p = klist + K;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + bar_off);
+  uint64_t *empty = full + kMaxStages;
+  uint64_t *accum = empty + kMaxStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * ROWS;
+  const int nsplit = gridDim.y, split = blockIdx.y;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  for (int k = tid; k < K; k += kTmaThreads) kflag[k] = 0;
+  __syncthreads();
+  for (int e = tid; e < ROWS * K; e += kTmaThreads) {
+    int r = e / K, k = e - r * K;
+    int v = -1;
+    if (row0 + r < n_rows) v = map ? __ldg(map + (int64_t)(row0 + r) * K + k) : row0 + r;
+    smap[e] = v;
+    if (v >= 0) kflag[k] = 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < K; ++k)
+      if (kflag[k]) klist[n++] = k;
+    const int per = (n + nsplit - 1) / nsplit;
+    const int lo = min(n, split * per), hi = min(n, lo + per);
+    for (int i = lo; i < hi; ++i) klist[i - lo] = klist[i];
+    *nk_p = hi - lo;
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<NT>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nk = *nk_p;
+  const int nkb = (Cin + 31) >> 5;
+  const int T = nk * nkb;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer (one warp, never waits for data)
+    for (int it = 0; it < T; ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(empty + s, ph ^ 1u);
+      const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
+      const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full + s, a_bytes + b_bytes);
+        tma_load_2d(b_st, &tmW, kb * 32, k * Cout, full + s);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < MSUB; ++m) {
+        const int r = m * 128 + lane * 4;
+        int i0 = smap[(r + 0) * K + k], i1 = smap[(r + 1) * K + k], i2 = smap[(r + 2) * K + k], i3 = smap[(r + 3) * K + k];
+        i0 = i0 < 0 ? n_in : i0; i1 = i1 < 0 ? n_in : i1; i2 = i2 < 0 ? n_in : i2; i3 = i3 < 0 ? n_in : i3;
+        tma_gather4(a_st + (uint32_t)r * 128, &tmA, kb * 32, i0, i1, i2, i3, full + s);
+      }
+    }
+  } else if (warp == 5 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    for (int it = 0; it < T; ++it) {
+      const int s = it % nstages;
+      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      const int kb = it % nkb;
+      const int kvalid = min(32, Cin - kb * 32);
+      const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
+#pragma unroll
+      for (int m = 0; m < MSUB; ++m)
+        for (int j = 0; j < (kvalid >> 3); ++j) {
+          const uint64_t ad = make_smem_desc(a_st + (uint32_t)m * (128 * 128) + j * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(b_st + j * 32, 16, 1024);
+          mma_tf32(tmem + (uint32_t)(m * Cout), ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+        }
+      mma_commit(empty + s);
+    }
+    mma_commit(accum);
+  }
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    if (T > 0) {
+      mbar_wait(accum, 0);
+      tc_fence_after();
+    }
+    const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+    for (int m = 0; m < MSUB; ++m) {
+      const int row = row0 + m * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < Cout; c0 += 16) {
+        float v[16];
+        if (T > 0) {
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * Cout + c0), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (row < n_rows) {
+          if (addend && split == 0) {
+            const float *ad = addend + (int64_t)row * ldadd + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(ad + i);
+          }
+          float *o = out + (int64_t)row * ldo + c0;
+          if (nsplit > 1) {
+            if (T > 0 || (addend && split == 0)) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) atomicAdd(o + i, v[i]);
+            }
+          } else if (vec) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4 *>(o + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = v[i];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<NT>(tmem);
+}
+
+template <uint32_t NT, int MSUB>
+static int launch_gather_tma(dim3 grid, const TcSmemLayout &L, int nstages, const CUtensorMap &tmA,
+                             const CUtensorMap &tmW, const int32_t *map, int64_t n_out, int64_t n_in, int K, int Cin,
+                             int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
+  auto kern = gather_conv_tma_kernel<NT, MSUB>;
+  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
+  kern<<<grid, kTmaThreads, L.total, st>>>(tmA, tmW, map, (int)n_out, (int)n_in, K, Cin, Cout, addend, ldadd, out, ldo,
+                                           nstages, idesc, L.map_off, L.klist_off, L.bar_off);
+  return 0;
+}
+
+int gather_conv_tma(const float *A, int64_t lda, int64_t n_in, const int32_t *map, int64_t n_out, int K,
+                    const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
+                    cudaStream_t st) {
+  if (n_out <= 0) return 0;
+  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && 2 * Cout <= 512) ? 2 : 1;
+  if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
+  int nstages = kMaxStages;
+  TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
+  while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(msub, Cout, K, --nstages);
+  if (L.total > 227 * 1024) return set_error("gather_conv_tma: shared memory %u too large", L.total);
+  const int64_t tiles = ceil_div(n_out, msub * 128);
+  int nsplit = 1;
+  if (K > 1 && tiles * 2 <= kNumSMs) {
+    nsplit = (int)min((int64_t)K, (int64_t)kNumSMs / tiles);
+    if (nsplit > 9) nsplit = 9;
+  }
+  if (const char *e = getenv("B200SCN_TC_NSPLIT")) nsplit = max(1, min(K, atoi(e)));  // test hook
+  if (nsplit > 1) {
+    if (ldo == Cout) SCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_out * Cout, st));
+    else SCN_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * Cout, (size_t)n_out, st));
+  }
+  alignas(64) CUtensorMap tmA, tmW;
+  if (make_tmap(&tmA, A, n_in, Cin, lda, 1)) return 1;                       // gather4: one row per box
+  if (make_tmap(&tmW, Wkm, (int64_t)K * Cout, Cin, Cin, Cout)) return 1;      // weight slice: Cout rows x 32 channels
+  dim3 grid((unsigned)tiles, (unsigned)nsplit);
+  const int cols = msub * Cout;
+#define SCN_ARGS grid, L, nstages, tmA, tmW, map, n_out, n_in, K, Cin, Cout, addend, ldadd, out, ldo, st
+  int rc;
+  if (msub == 2) {
+    if (cols <= 64) rc = launch_gather_tma<64, 2>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tma<128, 2>(SCN_ARGS);
+    else if (cols <= 256) rc = launch_gather_tma<256, 2>(SCN_ARGS);
+    else rc = launch_gather_tma<512, 2>(SCN_ARGS);
+  } else {
+    if (cols <= 32) rc = launch_gather_tma<32, 1>(SCN_ARGS);
+    else if (cols <= 64) rc = launch_gather_tma<64, 1>(SCN_ARGS);
+    else if (cols <= 128) rc = launch_gather_tma<128, 1>(SCN_ARGS);
+    else rc = launch_gather_tma<256, 1>(SCN_ARGS);
+  }
+#undef SCN_ARGS
+  if (rc) return rc;
+  SCN_CHECK_LAUNCH("gather_conv_tma");
   count_launch(1);
   return 0;
 }

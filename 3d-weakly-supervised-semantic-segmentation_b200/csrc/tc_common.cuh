@@ -135,3 +135,39 @@ __device__ __forceinline__ uint32_t sw128_32b(uint32_t r, uint32_t c) {
 
 }  // namespace tc
 }  // namespace b200scn
+
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor), sm_100a
+#include <cuda.h>
+
+namespace b200scn {
+namespace tc {
+
+// arm an mbarrier with the number of bytes the TMA engine will deliver to it, and arrive once
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// tiled 2-D load: box (set in the tensor map) at element coordinates {c0 (inner), c1 (row)}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// gather4: four rows (r0..r3, any order, out-of-range rows are zero-filled) x one box width at inner coordinate c0,
+// written as four consecutive rows of the (swizzled) shared-memory image
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tmap, int c0, int r0, int r1, int r2,
+                                            int r3, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
+      "%6}], [%7];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+}  // namespace tc
+}  // namespace b200scn

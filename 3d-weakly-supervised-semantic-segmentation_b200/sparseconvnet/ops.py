@@ -129,7 +129,7 @@ def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
     w = gw.kmajor() if tf32 else gw.rowmajor()
     tok = _p0("gather%d" % K, "conv_gather", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out if rules is None else rules, 8.0 if map_t is not None else 0.0, 2.0 * Cin * Cout)
-    check(lib.b200scn_gather_conv(ptr(x), ldx, ptr(map_t), n_out, K, ptr(w), Cin, Cout, ptr(addend), lda,
+    check(lib.b200scn_gather_conv(ptr(x), ldx, x.shape[0], ptr(map_t), n_out, K, ptr(w), Cin, Cout, ptr(addend), lda,
                                   ptr(out), Cout, 1 if tf32 else 0, _lib.stream_for(x)))
     _p1(tok)
     return out

@@ -77,6 +77,7 @@ int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, i
 
 /* ------------------------------------------------------------------ convolutions (A5-A7, A10) */
 /* out[o,:] = sum_k A[map[o*K+k],:] . W[k]  (+ addend[o,:] if addend)      W: (K,Cin,Cout) row-major.
+ * A has n_in rows (map values are in [0,n_in) or -1).
  * map NULL => K must be 1 and row o reads A[o] (NetworkInNetwork).
  * Replaces SubmanifoldConvolution_updateOutput / Convolution_updateOutput and, with the transposed
  * mirrored weights, SubmanifoldConvolution / Deconvolution backward-input.
@@ -84,7 +85,7 @@ int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, i
  *            1 = TF32 tensor cores (tcgen05.mma, fp32 accumulate in TMEM), W given K-major: (K,Cout,Cin) row-major;
  *                needs b200scn_gather_conv_tf32_ok(Cin, Cout, lda). */
 int b200scn_gather_conv_tf32_ok(int Cin, int Cout, int64_t lda);
-int b200scn_gather_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K,
+int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t *map, int64_t n_out, int K,
                         const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
                         float *out, int64_t ldo, int precision, void *stream);
 
