@@ -39,10 +39,12 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
     if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, W))
       return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 256, 16-byte aligned rows "
                        "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
-    const char *e = getenv("B200SCN_TC_TMA");   // 0 selects the cp.async producer variant
-    if (e && atoi(e) == 0)
-      return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
-    return gather_conv_tma(A, lda, n_in, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+    // B200SCN_TC_TMA=1 selects the TMA tile::gather4 producer variant.  Measured on B200 (profiles/r1_tma_gather4.txt):
+    // 128-byte gather4 boxes run at ~1 row / 15 cycles / SM, 2.2x slower than per-lane cp.async, so it is not the default.
+    const char *e = getenv("B200SCN_TC_TMA");
+    if (e && atoi(e) == 1)
+      return gather_conv_tma(A, lda, n_in, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
+    return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
   }
   return gather_conv_simt(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
 }

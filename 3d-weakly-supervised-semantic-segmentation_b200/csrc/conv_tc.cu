@@ -232,8 +232,9 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
   if (n_out <= 0) return 0;
   // 256-row CTAs (two accumulators share each weight stage) once there are enough rows to fill the chip twice over
-  // (eight producer warps then gather for one CTA per SM; the weight slice of every stage is fetched once per 256 rows)
-  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && 2 * Cout <= 512) ? 2 : 1;
+  // (eight producer warps then gather for one CTA per SM; the weight slice of every stage is fetched once per 256 rows;
+  //  measured: a win from Cout = 96 up, while Cout <= 64 is faster as two 128-row CTAs per SM)
+  int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && Cout > 64 && 2 * Cout <= 512) ? 2 : 1;
   if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
   int nstages = kMaxStages;
   TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
@@ -450,7 +451,7 @@ int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const i
 }  // namespace b200scn
 
 // =====================================================================================================================
-// TMA variant of the gather convolution (the default): the per-lane cp.async producers are replaced by ONE warp that
+// TMA variant of the gather convolution (opt-in, B200SCN_TC_TMA=1; measured slower, see abi_conv.cu): the per-lane cp.async producers are replaced by ONE warp that
 // issues tile::gather4 TMA copies -- each lane names four neighbour rows (absent neighbour = an out-of-range row index,
 // which the TMA unit zero-fills), so one warp instruction stages 128 gathered rows x 128 bytes, already in the
 // SWIZZLE_128B image tcgen05.mma reads -- plus one tiled TMA load for the weight slice.  Completion is counted in bytes

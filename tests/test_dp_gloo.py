@@ -1,0 +1,46 @@
+"""Scene-sharded data parallelism on CPU: world_size 2 over gloo.  The flat-gradient all-reduce must give
+every rank the mean of the per-rank gradients, and shards must partition the scenes."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "3d-weakly-supervised-semantic-segmentation_b200")
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, PKG)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from b200scn_dp import FlatGrads, shard_scenes
+    torch.manual_seed(0)                       # identical initial weights on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    flat = FlatGrads(net.parameters())
+    scenes = shard_scenes(5, rank, world)      # rank 0: 0,2,4   rank 1: 1,3
+    torch.manual_seed(100 + rank)
+    x = torch.randn(4 * len(scenes), 6)
+    flat.zero()
+    net(x).pow(2).mean().backward()
+    local = flat.flat.clone()
+    flat.allreduce_mean()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.allclose(flat.flat, sum(gathered) / world, atol=1e-7)
+    views = all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
+    out[rank] = (ok, views, scenes)
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0][0] and out[1][0]
+    assert out[0][1] and out[1][1]
+    assert sorted(out[0][2] + out[1][2]) == [0, 1, 2, 3, 4]

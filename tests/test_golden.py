@@ -1,0 +1,85 @@
+"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle):
+CPU: the oracle still reproduces them;  GPU: the CUDA path matches them (rulebooks bit-exact, floats rel 1e-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import keys_to_vox, rel_err
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _small_unet(ns):
+    from golden.make_golden import small_unet
+    return small_unet(ns, smooth=True)
+
+
+def test_oracle_reproduces_golden_rulebooks():
+    from oracle import scn_oracle as ref
+    g = np.load(os.path.join(G, "rulebooks.npz"))
+    pv, vox = ref.input_rules(g["coords"])
+    assert np.array_equal(pv, g["pv"]) and np.array_equal(vox, g["vox"])
+    assert np.array_equal(ref.subm_map(vox), g["nbr"])
+    parent, off, voxc = ref.strided(vox, 2)
+    assert np.array_equal(parent, g["parent"]) and np.array_equal(off, g["off"]) and np.array_equal(voxc, g["voxc"])
+    assert np.array_equal(ref.subm_map(voxc), g["nbr1"])
+
+
+def _load_net(ns, g):
+    net = _small_unet(ns)
+    sd = {k[len("param::"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param::")}
+    net.load_state_dict(sd)
+    return net
+
+
+def test_oracle_reproduces_golden_net():
+    from oracle import scn_oracle as ref
+    g = np.load(os.path.join(G, "small_unet.npz"))
+    net = _load_net(ref, g)
+    f = torch.from_numpy(g["feats"]).requires_grad_(True)
+    out = net([torch.from_numpy(g["coords"]), f])
+    assert rel_err(out, torch.from_numpy(g["logits"])) < 1e-5
+    out.backward(torch.from_numpy(g["grad_out"]))
+    assert rel_err(f.grad, torch.from_numpy(g["grad_feats"])) < 1e-4
+    for n, p in net.named_parameters():
+        assert rel_err(p.grad, torch.from_numpy(g["grad::" + n])) < 1e-4, n
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_rulebooks():
+    import sparseconvnet as scn
+    g = np.load(os.path.join(G, "rulebooks.npz"))
+    coords = torch.from_numpy(g["coords"])
+    x = scn.InputLayer(3, 4096, mode=4)([coords, torch.zeros(coords.shape[0], 3).cuda()])
+    md = x.metadata
+    assert np.array_equal(md.pv.cpu().numpy(), g["pv"])
+    assert np.array_equal(keys_to_vox(md.levels[4096].ukeys), g["vox"])
+    assert np.array_equal(md.levels[4096].subm_map().cpu().numpy(), g["nbr"])
+    d = md.get_down(4096, 2)
+    assert np.array_equal(d.parent.cpu().numpy(), g["parent"])
+    assert np.array_equal(d.off.cpu().numpy().astype(np.int32), g["off"])
+    assert np.array_equal(keys_to_vox(d.coarse.ukeys), g["voxc"])
+    assert np.array_equal(d.coarse.subm_map().cpu().numpy(), g["nbr1"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("tf32", 1e-3)])
+def test_gpu_matches_golden_net(precision, tol):
+    """north_star tolerance: fp32 forward logits, input gradient and weight gradients within rel 1e-3 (the TF32
+    tensor-core path is held to the same norm-wise bound on this net)."""
+    import sparseconvnet as scn
+    g = np.load(os.path.join(G, "small_unet.npz"))
+    scn.set_precision(precision)
+    try:
+        net = _load_net(scn, g).cuda()
+        f = torch.from_numpy(g["feats"]).cuda().requires_grad_(True)
+        out = net([torch.from_numpy(g["coords"]), f])
+        assert rel_err(out, torch.from_numpy(g["logits"])) < tol
+        out.backward(torch.from_numpy(g["grad_out"]).cuda())
+        assert rel_err(f.grad, torch.from_numpy(g["grad_feats"])) < tol
+        for n, p in net.named_parameters():
+            assert rel_err(p.grad, torch.from_numpy(g["grad::" + n])) < tol, n
+    finally:
+        scn.set_precision("fp32")

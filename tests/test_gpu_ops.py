@@ -9,7 +9,7 @@ TOL = 1e-4
 TOL_TF32 = 2e-3   # TF32 operands (10-bit mantissa), fp32 accumulate: the stated tensor-core tolerance
 
 
-@pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3"])
+@pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3", "tf32-tma"])
 def precision(request):
     """fp32 CUDA-core path, TF32 tcgen05 path, and the TF32 path with its large-level (256-row CTAs) and tiny-level
     (offsets split over CTAs) variants forced on, which the heuristics would not pick at test sizes."""
@@ -21,9 +21,12 @@ def precision(request):
         os.environ["B200SCN_TC_MSUB"] = "2"
     if name == "tf32-split3":
         os.environ["B200SCN_TC_NSPLIT"] = "3"
+    if name == "tf32-tma":
+        os.environ["B200SCN_TC_TMA"] = "1"
     yield "fp32" if name == "fp32" else "tf32"
     os.environ.pop("B200SCN_TC_MSUB", None)
     os.environ.pop("B200SCN_TC_NSPLIT", None)
+    os.environ.pop("B200SCN_TC_TMA", None)
     scn.set_precision("fp32")
 
 
