@@ -319,7 +319,7 @@ def main():
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--points", type=int, default=150000)
     ap.add_argument("--distinct", type=int, default=6, help="distinct pre-generated batches cycled through")
-    ap.add_argument("--precision", default=os.environ.get("B200SCN_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("B200SCN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
