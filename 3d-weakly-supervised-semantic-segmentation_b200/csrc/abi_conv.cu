@@ -37,12 +37,12 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
   if (n_out >= ((int64_t)1 << 31)) return set_error("gather_conv: too many rows");
   if (precision == 1) {
     if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, W))
-      return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 256, 16-byte aligned rows "
+      return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 1024, 16-byte aligned rows "
                        "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
     // B200SCN_TC_TMA=1 selects the TMA tile::gather4 producer variant.  Measured on B200 (profiles/r1_tma_gather4.txt):
     // 128-byte gather4 boxes run at ~1 row / 15 cycles / SM, 2.2x slower than per-lane cp.async, so it is not the default.
     const char *e = getenv("B200SCN_TC_TMA");
-    if (e && atoi(e) == 1)
+    if (e && atoi(e) == 1 && Cout <= 256)
       return gather_conv_tma(A, lda, n_in, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
     return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
   }
@@ -74,7 +74,7 @@ int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, co
 
 /* 1 if b200scn_gather_conv(precision = 1) accepts this shape */
 extern "C" int b200scn_gather_conv_tf32_ok(int Cin, int Cout, int64_t lda) {
-  return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 256 && (lda % 4 == 0);
+  return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 1024 && (lda % 4 == 0);
 }
 
 extern "C" int b200scn_set_device(int device) {

@@ -252,6 +252,117 @@ __global__ void unpool_bwd_kernel(const float *__restrict__ d_out, int64_t ldd,
   d_in[j * ldi + c] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stem kernels (the Cin = 3 SubmanifoldConvolution at models/SparseConvNet.py:62 and its backward).
+// K below the tensor-core granularity and pure bandwidth: one warp per site, lanes over the wide channel dimension.
+// ---------------------------------------------------------------------------------------------------------------
+// out[o][co] = sum_k sum_{ci<CI} A[map[o][k]][ci] * W[k][ci][co]          (CI <= 4, lanes over co)
+template <int CI>
+__global__ void __launch_bounds__(256)
+gather_smallcin_kernel(const float *__restrict__ A, int64_t lda, const int32_t *__restrict__ map, int n_rows, int K,
+                       const float *__restrict__ W, int Cout, const float *__restrict__ addend, int64_t ldadd,
+                       float *__restrict__ out, int64_t ldo) {
+  extern __shared__ float sw[];  // K*CI*Cout
+  for (int e = threadIdx.x; e < K * CI * Cout; e += blockDim.x) sw[e] = W[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = warp0; o < n_rows; o += nwarps) {
+    const int32_t *mrow = map ? map + o * K : nullptr;
+    int mine = (mrow && lane < K) ? __ldg(mrow + lane) : -1;   // K <= 32 entries of this row, one per lane
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+      const int co = c0 + lane;
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) {
+        const int idx = mrow ? __shfl_sync(0xffffffffu, mine, k) : (int)o;
+        if (idx < 0) continue;  // warp-uniform
+        const float *a = A + (int64_t)idx * lda;
+        if (co < Cout) {
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) acc = fmaf(__ldg(a + ci), sw[(k * CI + ci) * Cout + co], acc);
+        }
+      }
+      if (co < Cout) {
+        if (addend) acc += __ldg(addend + o * ldadd + co);
+        out[o * ldo + co] = acc;
+      }
+    }
+  }
+}
+
+// out[o][co] = sum_k sum_ci A[map[o][k]][ci] * W[k][ci][co]   with CO <= 4 outputs (backward-input of the stem):
+// lanes over ci, warp reduction at the end
+template <int CO>
+__global__ void __launch_bounds__(256)
+gather_smallcout_kernel(const float *__restrict__ A, int64_t lda, const int32_t *__restrict__ map, int n_rows, int K,
+                        const float *__restrict__ W, int Cin, float *__restrict__ out, int64_t ldo) {
+  extern __shared__ float sw[];  // K*Cin*CO
+  for (int e = threadIdx.x; e < K * Cin * CO; e += blockDim.x) sw[e] = W[e];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t o = warp0; o < n_rows; o += nwarps) {
+    const int32_t *mrow = map ? map + o * K : nullptr;
+    int mine = (mrow && lane < K) ? __ldg(mrow + lane) : -1;
+    float acc[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) acc[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int idx = mrow ? __shfl_sync(0xffffffffu, mine, k) : (int)o;
+      if (idx < 0) continue;
+      const float *a = A + (int64_t)idx * lda;
+      for (int ci = lane; ci < Cin; ci += 32) {
+        const float x = __ldg(a + ci);
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[j] = fmaf(x, sw[(k * Cin + ci) * CO + j], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CO; ++j) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], d);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < CO; ++j) out[o * ldo + j] = acc[j];
+    }
+  }
+}
+
+// dW[k][ca][cg] = sum_pairs A[pa][ca] * G[pg][cg]   with CA <= 4 (the stem's weight gradient): lanes over cg
+template <int CA>
+__global__ void __launch_bounds__(256)
+pair_dw_smallca_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ G, int64_t ldg,
+                       const int32_t *__restrict__ pair_a, const int32_t *__restrict__ pair_g,
+                       const int32_t *__restrict__ offsets, int n_single, int chunk, int Cg, float *__restrict__ dW) {
+  const int k = blockIdx.y;
+  const int beg = offsets ? offsets[k] : 0;
+  const int end = offsets ? offsets[k + 1] : n_single;
+  const int p0 = beg + blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, end);
+  if (p0 >= p1) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c0 = 0; c0 < Cg; c0 += 32) {
+    const int cg = c0 + lane;
+    float acc[CA];
+#pragma unroll
+    for (int j = 0; j < CA; ++j) acc[j] = 0.f;
+    for (int p = p0 + warp; p < p1; p += nw) {
+      const int ra = pair_a ? __ldg(pair_a + p) : p;
+      const int rg = pair_g ? __ldg(pair_g + p) : p;
+      const float g = cg < Cg ? __ldg(G + (int64_t)rg * ldg + cg) : 0.f;
+#pragma unroll
+      for (int j = 0; j < CA; ++j) acc[j] = fmaf(__ldg(A + (int64_t)ra * lda + j), g, acc[j]);
+    }
+    if (cg < Cg) {
+#pragma unroll
+      for (int j = 0; j < CA; ++j) atomicAdd(dW + ((int64_t)k * CA + j) * Cg + cg, acc[j]);
+    }
+  }
+}
+
 template <int MODE>
 static int launch_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n_rows, int K,
                             const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
@@ -279,6 +390,30 @@ static int launch_conv_simt(const float *A, int64_t lda, const int32_t *map, int
 int gather_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K,
                      const float *W, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
                      int64_t ldo, cudaStream_t st) {
+  if (n_out > 0 && K <= 32 && (Cin <= 4 || (Cout <= 4 && !addend))) {
+    const unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(n_out, 8));
+    const size_t smem = sizeof(float) * (size_t)K * Cin * Cout;
+    if (smem <= 48 * 1024) {
+      if (Cin <= 4) {
+        switch (Cin) {
+          case 1: gather_smallcin_kernel<1><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cout, addend, ldadd, out, ldo); break;
+          case 2: gather_smallcin_kernel<2><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cout, addend, ldadd, out, ldo); break;
+          case 3: gather_smallcin_kernel<3><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cout, addend, ldadd, out, ldo); break;
+          default: gather_smallcin_kernel<4><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cout, addend, ldadd, out, ldo); break;
+        }
+      } else {
+        switch (Cout) {
+          case 1: gather_smallcout_kernel<1><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cin, out, ldo); break;
+          case 2: gather_smallcout_kernel<2><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cin, out, ldo); break;
+          case 3: gather_smallcout_kernel<3><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cin, out, ldo); break;
+          default: gather_smallcout_kernel<4><<<blocks, 256, smem, st>>>(A, lda, map, (int)n_out, K, W, Cin, out, ldo); break;
+        }
+      }
+      SCN_CHECK_LAUNCH("gather_small");
+      count_launch(1);
+      return 0;
+    }
+  }
   return launch_conv_simt<0>(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, st);
 }
 int scatter_conv_simt(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,
@@ -291,6 +426,21 @@ int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const
                  int Cg, float *dW, cudaStream_t st) {
   SCN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * Ca * Cg, st));
   if (n_pairs_max <= 0) return 0;
+  if (Ca <= 4) {
+    int64_t want = ceil_div((int64_t)kNumSMs * 8, (int64_t)K);
+    int64_t ch = ceil_div(n_pairs_max, want > 0 ? want : 1);
+    if (ch < 256) ch = 256;
+    dim3 g((unsigned)ceil_div(n_pairs_max, ch), (unsigned)K);
+    switch (Ca) {
+      case 1: pair_dw_smallca_kernel<1><<<g, 256, 0, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, (int)ch, Cg, dW); break;
+      case 2: pair_dw_smallca_kernel<2><<<g, 256, 0, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, (int)ch, Cg, dW); break;
+      case 3: pair_dw_smallca_kernel<3><<<g, 256, 0, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, (int)ch, Cg, dW); break;
+      default: pair_dw_smallca_kernel<4><<<g, 256, 0, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, (int)ch, Cg, dW); break;
+    }
+    SCN_CHECK_LAUNCH("pair_dw_smallca");
+    count_launch(1);
+    return 0;
+  }
   const int tiles_a = (int)ceil_div(Ca, 64), tiles_g = (int)ceil_div(Cg, 64);
   // aim for ~8 CTAs per SM overall; chunk is a multiple of BK
   int64_t want_chunks = ceil_div((int64_t)kNumSMs * 8, (int64_t)K * tiles_a * tiles_g);

@@ -24,6 +24,40 @@ namespace b200scn {
 
 using namespace tc;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: rows x cols (cols contiguous, row pitch ld floats), box = box_rows x 32 floats, 128-byte swizzle
+static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %d ld %lld box %d", (int)r,
+                                          (long long)rows, cols, (long long)ld, box_rows);
+  return 0;
+}
+
 constexpr int kTcThreads = 160;
 constexpr int kMaxStages = 4;
 
@@ -47,10 +81,11 @@ static TcSmemLayout tc_layout(int msub, int Cout, int K, int nstages) {
 // (the producers are bound by their own dependent issue chain, so 16 warps beat 4 by ~3x: profiles/).
 template <uint32_t NT, int MSUB, int NPW>
 __global__ void __launch_bounds__(32 * (NPW + 1))
-gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *__restrict__ map, int n_rows, int K,
-                      const float *__restrict__ Wkm, int Cin, int Cout, const float *__restrict__ addend,
+gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
+                      const int32_t *__restrict__ map, int n_rows, int K, int Cin, int Cout,
+                      const float *__restrict__ addend,
                       int64_t ldadd, float *__restrict__ out, int64_t ldo, int nstages, uint32_t idesc,
-                      uint32_t map_off, uint32_t klist_off, uint32_t bar_off) {
+                      uint32_t map_off, uint32_t klist_off, uint32_t bar_off, int w_rows_per_k, int w_row0) {
   constexpr int ROWS = MSUB * 128;
   constexpr int NTHREADS = 32 * (NPW + 1);
   constexpr int WPS = NPW / 4;  // producer warps per stage
@@ -93,11 +128,12 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
     for (int i = lo; i < hi; ++i) klist[i - lo] = klist[i];
     *nk_p = hi - lo;
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(full + s, 32 * WPS);
+      mbar_init(full + s, 32 * WPS + 1);   // every gathering lane + the weight TMA's expect_tx arrival
       mbar_init(empty + s, 1);
     }
     mbar_init(accum, 1);
     fence_barrier_init();
+    tma_prefetch_desc(&tmW);
   }
   if (warp == NPW) tmem_alloc<NT>(tmem_slot);
   tc_fence_before();
@@ -117,7 +153,13 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
     const int my_stage = warp % nstages, half = warp / nstages;
     if (half < WPS) {
       constexpr int RPW = ROWS / WPS;  // rows per producer warp
+      constexpr int NI = RPW / 4;      // row slots per lane (8 lanes share a row)
       const int rbase = half * RPW;
+      // Absent neighbours need a ZERO row, not a copy: `dirty` remembers which of this lane's row slots of this stage
+      // buffer currently hold data (the warp owns the same rows of the same buffer for the whole tile), so a slot is
+      // touched only when it receives data or when stale data must be cleared -- at 2 cm voxels 60-80 % of the
+      // (row, offset) slots are absent and stay untouched.
+      uint32_t dirty = 0xFFFFFFFFu;    // unknown contents on first use
       for (int it = my_stage; it < T; it += nstages) {
         const int s = my_stage;
         const uint32_t ph = (uint32_t)(it / nstages) & 1u;
@@ -125,21 +167,26 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
         const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
         const int chan = kb * 32 + c * 4;
         const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
+        if (half == 0 && lane == 0) {   // weight slice W[k][:, kb*32 .. +32): one tiled TMA load, counted in bytes
+          mbar_arrive_expect_tx(full + s, b_bytes);
+          tma_load_2d(b_st, &tmW, kb * 32, k * w_rows_per_k + w_row0, full + s);
+        }
         if (chan < Cin) {
           const float *acol = A + chan;
-#pragma unroll 8
-          for (int i = 0; i < RPW / 4; ++i) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
             const int r = rbase + rl + 4 * i;
             const int idx = smap[r * K + k];
-            cp_async16(a_st + sw128(r, c), idx >= 0 ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
-                       idx >= 0 ? 16u : 0u);
+            const bool valid = idx >= 0;
+            if (valid || ((dirty >> i) & 1u))
+              cp_async16(a_st + sw128(r, c), valid ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
+                         valid ? 16u : 0u);
+            dirty = valid ? (dirty | (1u << i)) : (dirty & ~(1u << i));
           }
-          const float *wk = Wkm + (int64_t)k * Cout * Cin + chan;
-          for (int n = rl + 4 * half; n < Cout; n += 4 * WPS) cp_async16(b_st + sw128(n, c), wk + (int64_t)n * Cin, 16u);
         }
         cp_async_wait_all();
         fence_proxy_async();
-        mbar_arrive(full + s);   // (measured: one elected arrival per warp after __syncwarp is 30 % slower)
+        mbar_arrive(full + s);
       }
     }
   } else if (lane == 0) {
@@ -213,24 +260,44 @@ gather_conv_tc_kernel(const float *__restrict__ A, int64_t lda, const int32_t *_
 }
 
 bool gather_conv_tc_supported(const float *A, int64_t lda, int K, int Cin, int Cout, const float *W) {
-  return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 256 && (lda % 4 == 0) && K <= 64 &&
+  return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 1024 && (lda % 4 == 0) && K <= 64 &&
          ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
 }
 
 template <uint32_t NT, int MSUB, int NPW>
 static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const float *A, int64_t lda,
                             const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin, int Cout,
-                            const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k, int w_row0,
+                            cudaStream_t st) {
   auto kern = gather_conv_tc_kernel<NT, MSUB, NPW>;
   SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
-  kern<<<grid, 32 * (NPW + 1), L.total, st>>>(A, lda, map, (int)n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, nstages,
-                                          idesc, L.map_off, L.klist_off, L.bar_off);
+  alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (K*Cout_total, Cin) K-major stack
+  if (make_tmap(&tmW, Wkm, (int64_t)K * w_rows_per_k, Cin, Cin, Cout)) return 1;
+  kern<<<grid, 32 * (NPW + 1), L.total, st>>>(tmW, A, lda, map, (int)n_out, K, Cin, Cout, addend, ldadd, out, ldo,
+                                              nstages, idesc, L.map_off, L.klist_off, L.bar_off, w_rows_per_k, w_row0);
   return 0;
 }
 
+static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm,
+                               int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
+                               int w_rows_per_k, int w_row0, cudaStream_t st);
+
+// output channels beyond 256 (the widest tcgen05 N) are produced by separate launches over column slices
 int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin,
                    int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
+  for (int n0 = 0; n0 < Cout; n0 += 256) {
+    const int nc = Cout - n0 < 256 ? Cout - n0 : 256;
+    if (gather_conv_tc_part(A, lda, map, n_out, K, Wkm, Cin, nc, addend ? addend + n0 : nullptr, ldadd, out + n0, ldo,
+                            Cout, n0, st))
+      return 1;
+  }
+  return 0;
+}
+
+static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, int64_t n_out, int K, const float *Wkm,
+                               int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
+                               int w_rows_per_k, int w_row0, cudaStream_t st) {
   if (n_out <= 0) return 0;
   // 256-row CTAs (two accumulators share each weight stage) once there are enough rows to fill the chip twice over
   // (eight producer warps then gather for one CTA per SM; the weight slice of every stage is fetched once per 256 rows;
@@ -256,7 +323,7 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
   dim3 grid((unsigned)tiles, (unsigned)nsplit);
   const int cols = msub * Cout;
   int rc;
-#define SCN_ARGS grid, L, nstages, A, lda, map, n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, st
+#define SCN_ARGS grid, L, nstages, A, lda, map, n_out, K, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
   if (msub == 2) {
     if (cols <= 64) rc = launch_gather_tc<64, 2, 16>(SCN_ARGS);
     else if (cols <= 128) rc = launch_gather_tc<128, 2, 16>(SCN_ARGS);
@@ -289,13 +356,18 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
 namespace b200scn {
 
 constexpr int kDwPairs = 32;  // pairs per stage (4 MMAs of K = 8)
+constexpr int kDwWarps = 8;   // producer warps, two per stage
 
+// A stage holds only the VALID 32-channel blocks of A (ab of them) followed by the gb blocks of G.  The M = 128 MMA of
+// tile t still reads four MN blocks starting at block 4t; blocks past Ca alias whatever follows in shared memory
+// (G blocks, the next stage, the tail pad) -- finite or not, they only feed accumulator rows >= Ca, which are never read.
 template <uint32_t NT>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(32 * (kDwWarps + 1))
 pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ G, int64_t ldg,
                   const int32_t *__restrict__ pair_a, const int32_t *__restrict__ pair_g,
                   const int32_t *__restrict__ offsets, int n_single, int chunk, int Ca, int Cg, int nstages,
-                  uint32_t idesc, float *__restrict__ dW) {
+                  uint32_t idesc, float *__restrict__ dW, int64_t dw_kstride) {
+  constexpr int NPW = kDwWarps;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -304,9 +376,10 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   const int ab = (Ca + 31) >> 5;             // valid 32-channel blocks of A
   const int gb = (Cg + 31) >> 5;
   const uint32_t blk = kDwPairs * 128;       // one 32-channel block of one stage: 32 pair rows x 128 B
-  const uint32_t a_bytes = (uint32_t)(4 * mt) * blk, g_bytes = (uint32_t)gb * blk;
+  const uint32_t a_bytes = (uint32_t)ab * blk, g_bytes = (uint32_t)gb * blk;
   const uint32_t stage_bytes = a_bytes + g_bytes;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sm + (uint32_t)nstages * stage_bytes);
+  // barriers sit after the stages and a 3-block pad (the aliasing reads above may run 3 blocks past the last stage)
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + (uint32_t)nstages * stage_bytes + 3 * blk);
   uint64_t *empty = full + kMaxStages;
   uint64_t *accum = empty + kMaxStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
@@ -319,32 +392,35 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   const int p1 = min(p0 + chunk, end);
   if (p0 >= p1) return;  // uniform for the whole CTA
   const int T = (p1 - p0 + kDwPairs - 1) / kDwPairs;
+  const int wps = NPW / nstages;  // producer warps per stage (nstages is 2 or 4)
 
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(full + s, 32);
+      mbar_init(full + s, 32 * wps);
       mbar_init(empty + s, 1);
     }
     mbar_init(accum, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<NT>(tmem_slot);
+  if (warp == NPW) tmem_alloc<NT>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < NPW) {
+    // producers: stage s is always filled by warps s, s + nstages, ... (each takes an equal share of the 32 pairs)
     const int c = lane & 7, rl = lane >> 3;
-    for (int it = warp; it < T && warp < nstages; it += nstages) {
-      const int s = it % nstages;
+    const int my_stage = warp % nstages, part = warp / nstages;
+    const int rows_per_warp = kDwPairs / wps;
+    for (int it = my_stage; it < T; it += nstages) {
+      const int s = my_stage;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(empty + s, ph ^ 1u);
       const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
       const int pbase = p0 + it * kDwPairs;
-#pragma unroll 2
-      for (int i = 0; i < kDwPairs / 4; ++i) {
-        const int r = rl + 4 * i;
+      for (int i = 0; i < rows_per_warp / 4; ++i) {
+        const int r = part * rows_per_warp + rl + 4 * i;
         const int p = pbase + r;
         const bool live = p < p1;
         const int ra = live ? (pair_a ? __ldg(pair_a + p) : p) : 0;
@@ -383,15 +459,16 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
     mma_commit(accum);
   }
 
-  if (warp < 4) {
+  if (warp < NPW) {
     mbar_wait(accum, 0);
     tc_fence_after();
-    float *Wk = dW + (int64_t)k * Ca * Cg;
-    for (int t = 0; t < mt; ++t) {
-      const int ca = t * 128 + warp * 32 + lane;
+    float *Wk = dW + (int64_t)k * dw_kstride;
+    const int q = warp & 3;
+    for (int t = warp >> 2; t < mt; t += NPW / 4) {   // warps 0-3: even tiles' lane quarters, warps 4-7: odd tiles'
+      const int ca = t * 128 + q * 32 + lane;
       for (int c0 = 0; c0 < Cg; c0 += 16) {
         float v[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * Cg + c0), v);
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * Cg + c0), v);
         if (ca < Ca) {
           float *o = Wk + (int64_t)ca * Cg + c0;
 #pragma unroll
@@ -402,25 +479,24 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<NT>(tmem);
+  if (warp == NPW) tmem_dealloc<NT>(tmem);
 }
 
 bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg) {
-  return (Ca % 4 == 0) && (Cg % 16 == 0) && Cg >= 16 && Cg <= 256 && Ca >= 4 && Ca <= 256 && (lda % 4 == 0) &&
-         (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
-         (((Ca + 127) >> 7) * Cg <= 512);
+  return (Ca % 4 == 0) && (Cg % 16 == 0) && Cg >= 16 && Cg <= 256 && Ca >= 4 && (lda % 4 == 0) && (ldg % 4 == 0) &&
+         ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0);
 }
 
-int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
-               const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
-               float *dW, cudaStream_t st) {
-  SCN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * Ca * Cg, st));
-  if (n_pairs_max <= 0) return 0;
-  const int mt = (Ca + 127) >> 7, gb = (Cg + 31) >> 5;
-  const uint32_t stage_bytes = (uint32_t)(4 * mt + gb) * kDwPairs * 128;
+// one launch for channels [ca0, ca0 + Ca) of A (the accumulator of a launch must fit the 512 TMEM columns)
+static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                           const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
+                           float *dW, int64_t dw_kstride, cudaStream_t st) {
+  const int mt = (Ca + 127) >> 7, ab = (Ca + 31) >> 5, gb = (Cg + 31) >> 5;
+  const uint32_t blk = kDwPairs * 128;
+  const uint32_t stage_bytes = (uint32_t)(ab + gb) * blk;
   int nstages = kMaxStages;
-  while (nstages > 2 && (uint32_t)nstages * stage_bytes + 256 + 1024 > 100 * 1024) --nstages;
-  const uint32_t smem = (uint32_t)nstages * stage_bytes + 256 + 1024;
+  if ((uint32_t)nstages * stage_bytes + 3 * blk + 256 + 1024 > 72 * 1024) nstages = 2;   // keep >= 3 CTAs per SM
+  const uint32_t smem = (uint32_t)nstages * stage_bytes + 3 * blk + 256 + 1024;
   if (smem > 227 * 1024) return set_error("pair_dw_tc: shared memory %u too large", smem);
   // chunk of pairs per CTA: enough CTAs for ~4 per SM overall, a multiple of the stage size
   int64_t want_chunks = ceil_div((int64_t)kNumSMs * 4, (int64_t)K);
@@ -435,8 +511,8 @@ int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const i
   do {                                                                                                           \
     auto kern = pair_dw_tc_kernel<NT>;                                                                           \
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    kern<<<grid, kTcThreads, smem, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max,          \
-                                         (int)chunk, Ca, Cg, nstages, idesc, dW);                                \
+    kern<<<grid, 32 * (kDwWarps + 1), smem, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, \
+                                                  (int)chunk, Ca, Cg, nstages, idesc, dW, dw_kstride);           \
   } while (0)
   if (cols <= 32) SCN_LAUNCH_DW(32);
   else if (cols <= 64) SCN_LAUNCH_DW(64);
@@ -446,6 +522,23 @@ int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const i
 #undef SCN_LAUNCH_DW
   SCN_CHECK_LAUNCH("pair_dw_tc");
   count_launch(1);
+  return 0;
+}
+
+int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+               const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
+               float *dW, cudaStream_t st) {
+  SCN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * Ca * Cg, st));
+  if (n_pairs_max <= 0) return 0;
+  // channel slices of A whose accumulators fit TMEM: 128-channel tiles x Cg columns <= 512
+  const int max_tiles = 512 / Cg >= 1 ? 512 / Cg : 1;
+  const int slice = 128 * (max_tiles > 4 ? 4 : max_tiles);
+  for (int ca0 = 0; ca0 < Ca; ca0 += slice) {
+    const int ca = Ca - ca0 < slice ? Ca - ca0 : slice;
+    if (pair_dw_tc_part(A + ca0, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, ca, Cg,
+                        dW + (int64_t)ca0 * Cg, (int64_t)Ca * Cg, st))
+      return 1;
+  }
   return 0;
 }
 
@@ -460,40 +553,6 @@ int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const i
 // pipe.  Warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer.
 // =====================================================================================================================
 namespace b200scn {
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// 2-D fp32 tensor map: rows x cols (cols contiguous, row pitch ld floats), box = box_rows x 32 floats, 128-byte swizzle
-static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %d ld %lld box %d", (int)r,
-                                          (long long)rows, cols, (long long)ld, box_rows);
-  return 0;
-}
 
 constexpr int kTmaThreads = 192;
 

@@ -81,6 +81,7 @@ class Down:
         self.s, self.K, self.fine, self.coarse, self.parent, self.off = s, s ** 3, fine, coarse, parent, off
         self.child = None
         self.pairs = None
+        self.onehot = None
 
     def child_map(self):
         if self.child is None:
@@ -90,6 +91,16 @@ class Down:
             check(lib.b200scn_child_map(ptr(self.parent), ptr(self.off), self.fine.n, None, self.K,
                                         ptr(self.child), self.coarse.n, st))
         return self.child
+
+    def onehot_map(self):
+        """fine-side view of the same rulebook: onehot[i][k] = parent[i] if off[i] == k else -1, so that
+        out[i] = in[parent[i]] @ W[off[i]] runs through the output-stationary gather kernel (tensor-core path)."""
+        if self.onehot is None:
+            oh = alloc_rows(self.fine.n, self.K, self.parent.device, torch.int32)
+            oh.fill_(-1)
+            oh.scatter_(1, self.off.long().unsqueeze(1), self.parent.unsqueeze(1))
+            self.onehot = oh
+        return self.onehot
 
     def child_pairs(self):
         """pair_in = fine ids, pair_out = coarse ids, grouped by offset."""

@@ -135,9 +135,12 @@ def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
     return out
 
 
-def scatter_conv(x, map_t, n_out, K, gw):
-    """out[map[j,k]] = x[j] @ Wg[k]; every out row is addressed exactly once by a strided child map."""
+def scatter_conv(x, map_t, n_out, K, gw, down=None):
+    """out[map[j,k]] = x[j] @ Wg[k]; every out row is addressed exactly once by a strided child map.
+    On the tensor-core path the same product is computed output-stationary through the one-hot fine-side map."""
     x, ldx = _c(x)
+    if down is not None and _use_tf32(gw, ldx, x):
+        return gather_conv(x, down.onehot_map(), n_out, K, gw, rules=n_out)
     w = gw.rowmajor()
     Cin, Cout = gw.cin, gw.cout
     out = alloc_rows(n_out, Cout, x.device)
@@ -203,7 +206,7 @@ class ConvolutionFn(torch.autograd.Function):
         down = ctx.down
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True))
+            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True), down)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
             dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
@@ -218,7 +221,7 @@ class DeconvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w))
+        return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w), down)
 
     @staticmethod
     def backward(ctx, g):

@@ -60,7 +60,7 @@ def _check(mg, mr, xg, xr, fg, fr, dense_out=False, TOL=TOL):
         assert rel_err(pg.grad, pr.grad) < TOL, n
 
 
-@pytest.mark.parametrize("cin,cout", [(3, 16), (16, 16), (32, 32), (48, 80), (64, 32), (5, 7), (224, 224), (128, 64), (64, 192)])
+@pytest.mark.parametrize("cin,cout", [(3, 16), (16, 16), (32, 32), (48, 80), (64, 32), (5, 7), (224, 224), (128, 64), (64, 192), (384, 192), (320, 160)])
 def test_submanifold_conv(cin, cout, precision):
     coords, feats = random_cloud(cin * 100 + cout, 3000, 24, 2)
     scn, ref, xg, xr, fg, fr = _pair(coords, feats, cin)
