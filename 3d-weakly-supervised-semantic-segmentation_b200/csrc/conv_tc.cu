@@ -163,7 +163,7 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
       for (int it = my_stage; it < T; it += nstages) {
         const int s = my_stage;
         const uint32_t ph = (uint32_t)(it / nstages) & 1u;
-        mbar_wait(empty + s, ph ^ 1u);
+        mbar_wait_sleep(empty + s, ph ^ 1u, 500);
         const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
         const int chan = kb * 32 + c * 4;
         const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
@@ -184,6 +184,8 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
             dirty = valid ? (dirty | (1u << i)) : (dirty & ~(1u << i));
           }
         }
+        // (measured and rejected, profiles/r1_experiments.md: L2 prefetch one round ahead, software-pipelined producer
+        //  groups, one elected mbarrier arrival per warp, two stages with more CTAs per SM)
         cp_async_wait_all();
         fence_proxy_async();
         mbar_arrive(full + s);
@@ -214,8 +216,9 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
   if (warp < NPW) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
     // warp w may only read TMEM lanes 32*(w%4)..+31; with 8 producer warps, warps 4-7 take the second sub-tile
-    if (T > 0) {
-      mbar_wait(accum, 0);
+    const bool has_epilogue = (warp >> 2) < MSUB;   // the other producer warps go straight to the final barrier
+    if (T > 0 && has_epilogue) {
+      mbar_wait_sleep(accum, 0, 2000);
       tc_fence_after();
     }
     const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;

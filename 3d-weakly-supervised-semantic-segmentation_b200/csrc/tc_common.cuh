@@ -34,6 +34,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// same, but the waiting thread may be suspended by the hardware for up to `ns` per probe instead of spinning:
+// dozens of producer / epilogue warps polling an mbarrier otherwise eat the issue slots the working warps need
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!ok);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -125,6 +139,8 @@ __device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(gptr), "r"(src_bytes) : "memory");
 }
+// fire-and-forget fetch of the 128-byte line holding `gptr` into L2 (no register, no shared memory, no completion)
+__device__ __forceinline__ void prefetch_l2(const void *gptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gptr)); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // swizzled byte offset of 16-byte chunk c in row r of a [rows x 128 B] SWIZZLE_128B image
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
