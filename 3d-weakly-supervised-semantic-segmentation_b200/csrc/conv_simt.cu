@@ -228,28 +228,46 @@ pair_dw_simt_kernel(const float *__restrict__ A, int64_t lda, const float *__res
   }
 }
 
-__global__ void unpool_kernel(const float *__restrict__ in, int64_t ldi, const int32_t *__restrict__ parent,
-                              int64_t n_fine, int C, float *__restrict__ out, int64_t ldo) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_fine * C) return;
-  int64_t i = t / C;
-  int c = (int)(t - i * C);
-  out[i * ldo + c] = __ldg(in + (int64_t)__ldg(parent + i) * ldi + c);
+template <int VEC>
+__global__ void __launch_bounds__(256)
+unpool_kernel(const float *__restrict__ in, int64_t ldi, const int32_t *__restrict__ parent, int64_t n_fine, int C,
+              float *__restrict__ out, int64_t ldo) {
+  const int cv = C / VEC;
+  const int64_t total = n_fine * cv;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / cv;
+    const int c = (int)(t - i * cv) * VEC;
+    const float *src = in + (int64_t)__ldg(parent + i) * ldi + c;
+    if (VEC == 4) *reinterpret_cast<float4 *>(out + i * ldo + c) = __ldg(reinterpret_cast<const float4 *>(src));
+    else out[i * ldo + c] = __ldg(src);
+  }
 }
 
-__global__ void unpool_bwd_kernel(const float *__restrict__ d_out, int64_t ldd,
-                                  const int32_t *__restrict__ child, int64_t n_coarse, int K, int C,
-                                  float *__restrict__ d_in, int64_t ldi) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_coarse * C) return;
-  int64_t j = t / C;
-  int c = (int)(t - j * C);
-  float s = 0.f;
-  for (int k = 0; k < K; ++k) {
-    int i = __ldg(child + j * K + k);
-    if (i >= 0) s += __ldg(d_out + (int64_t)i * ldd + c);
+template <int VEC>
+__global__ void __launch_bounds__(256)
+unpool_bwd_kernel(const float *__restrict__ d_out, int64_t ldd, const int32_t *__restrict__ child, int64_t n_coarse,
+                  int K, int C, float *__restrict__ d_in, int64_t ldi) {
+  const int cv = C / VEC;
+  const int64_t total = n_coarse * cv;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = t / cv;
+    const int c = (int)(t - j * cv) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const int i = __ldg(child + j * K + k);
+      if (i < 0) continue;
+      if (VEC == 4) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(d_out + (int64_t)i * ldd + c));
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      } else {
+        acc[0] += __ldg(d_out + (int64_t)i * ldd + c);
+      }
+    }
+    if (VEC == 4) *reinterpret_cast<float4 *>(d_in + j * ldi + c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else d_in[j * ldi + c] = acc[0];
   }
-  d_in[j * ldi + c] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -462,10 +480,19 @@ using namespace b200scn;
 
 extern "C" {
 
+static bool vec4_ok(int C, int64_t lda, int64_t ldb, const void *a, const void *b) {
+  return C % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+
 int b200scn_unpool(const float *in, int64_t ldi, const int32_t *parent, int64_t n_fine, int C,
                    float *out, int64_t ldo, void *stream) {
   if (n_fine <= 0) return 0;
-  unpool_kernel<<<(unsigned)ceil_div(n_fine * C, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, parent, n_fine, C, out, ldo);
+  const bool vec = vec4_ok(C, ldi, ldo, in, out);
+  const int64_t total = n_fine * (vec ? C / 4 : C);
+  const unsigned blocks = (unsigned)min((int64_t)1 << 30, ceil_div(total, 256));   // one element group per thread
+  if (vec) unpool_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, ldi, parent, n_fine, C, out, ldo);
+  else unpool_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(in, ldi, parent, n_fine, C, out, ldo);
   SCN_CHECK_LAUNCH("unpool");
   count_launch(1);
   return 0;
@@ -474,7 +501,11 @@ int b200scn_unpool(const float *in, int64_t ldi, const int32_t *parent, int64_t 
 int b200scn_unpool_bwd(const float *d_out, int64_t ldd, const int32_t *child, int64_t n_coarse, int K,
                        int C, float *d_in, int64_t ldi, void *stream) {
   if (n_coarse <= 0) return 0;
-  unpool_bwd_kernel<<<(unsigned)ceil_div(n_coarse * C, 256), 256, 0, (cudaStream_t)stream>>>(d_out, ldd, child, n_coarse, K, C, d_in, ldi);
+  const bool vec = vec4_ok(C, ldd, ldi, d_out, d_in);
+  const int64_t total = n_coarse * (vec ? C / 4 : C);
+  const unsigned blocks = (unsigned)min((int64_t)1 << 30, ceil_div(total, 256));   // one element group per thread
+  if (vec) unpool_bwd_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ldd, child, n_coarse, K, C, d_in, ldi);
+  else unpool_bwd_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, ldd, child, n_coarse, K, C, d_in, ldi);
   SCN_CHECK_LAUNCH("unpool_bwd");
   count_launch(1);
   return 0;

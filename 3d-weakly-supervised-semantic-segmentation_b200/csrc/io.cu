@@ -65,6 +65,57 @@ __global__ void output_features_kernel(const float *__restrict__ feats, int64_t 
   }
 }
 
+// points grouped by site (counting sort): start[v] = first slot of site v, rows[start[v] .. start[v]+count[v]) = its rows.
+// The order inside a site is the arrival order of the atomics (any order gives the same set).
+__global__ void site_rows_kernel(const int32_t *__restrict__ pv, int64_t P, const int32_t *__restrict__ start,
+                                 int32_t *__restrict__ cursor, int32_t *__restrict__ rows) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= P) return;
+  const int v = __ldg(pv + r);
+  rows[__ldg(start + v) + atomicAdd(cursor + v, 1)] = (int32_t)r;
+}
+
+struct CountLoader {
+  const int32_t *count;
+  __device__ int live(int n) const { return n; }
+  __device__ int operator()(int64_t i) const { return count[i]; }
+};
+struct StartWriter {
+  int32_t *start;
+  __device__ void operator()(int64_t i, int c, int pos) const { start[i] = pos; }
+};
+
+// d_feats[v,:] = sum over the rows of site v of sel(row) * d_out[row,:]  -- gather, no atomics, every d_out row read once
+template <int VEC>
+__global__ void __launch_bounds__(256)
+output_features_bwd_csr_kernel(const float *__restrict__ d_out, int64_t N, int C, const int32_t *__restrict__ start,
+                               const int32_t *__restrict__ count, const int32_t *__restrict__ rows,
+                               const int32_t *first_row, const int32_t *last_row, int mode,
+                               float *__restrict__ d_feats, int64_t ldf) {
+  const int cv = C / VEC;
+  const int64_t total = N * cv;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = t / cv;
+    const int c0 = (int)(t - v * cv) * VEC;
+    const int s0 = __ldg(start + v), n = __ldg(count + v);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int q = 0; q < n; ++q) {
+      const int r = __ldg(rows + s0 + q);
+      if (output_sel(mode, r, (int)v, first_row, last_row) == 0.f) continue;
+      if (VEC == 4) {
+        float4 a = __ldg(reinterpret_cast<const float4 *>(d_out + (int64_t)r * C + c0));
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      } else {
+        acc[0] += __ldg(d_out + (int64_t)r * C + c0);
+      }
+    }
+    if (VEC == 4) *reinterpret_cast<float4 *>(d_feats + v * ldf + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else d_feats[v * ldf + c0] = acc[0];
+  }
+}
+
 __global__ void output_features_bwd_kernel(const float *__restrict__ d_out, int64_t P, int C,
                                            const int32_t *__restrict__ pv, const int32_t *first_row,
                                            const int32_t *last_row, int mode, float *d_feats,
@@ -133,6 +184,49 @@ int b200scn_output_features_bwd(const float *d_out, int64_t P, int C, const int3
   if (P * C <= 0) return 0;
   output_features_bwd_kernel<<<(unsigned)ceil_div(P * C, 256), 256, 0, (cudaStream_t)stream>>>(d_out, P, C, pv, first_row, last_row, mode, d_feats, ldf);
   SCN_CHECK_LAUNCH("output_features_bwd");
+  count_launch(1);
+  return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+size_t b200scn_site_rows_scratch_bytes(int64_t n_sites) {
+  return sizeof(int32_t) * ((size_t)(n_sites > 0 ? n_sites : 1) + scan_scratch_ints(n_sites) + 64);
+}
+
+int b200scn_site_rows(const int32_t *pv, int64_t P, const int32_t *count, int64_t n_sites, int32_t *start,
+                      int32_t *rows, void *scratch, size_t scratch_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (scratch_bytes < b200scn_site_rows_scratch_bytes(n_sites)) return set_error("site_rows: scratch too small");
+  if (n_sites <= 0 || P <= 0) return 0;
+  int32_t *cursor = (int32_t *)scratch;
+  int32_t *block_sums = cursor + n_sites;
+  SCN_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n_sites, st));
+  CountLoader ld{count};
+  StartWriter wr{start};
+  if (scan_flags(ld, wr, n_sites, nullptr, block_sums, nullptr, st)) return 1;
+  site_rows_kernel<<<(unsigned)ceil_div(P, 256), 256, 0, st>>>(pv, P, start, cursor, rows);
+  SCN_CHECK_LAUNCH("site_rows");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_output_features_bwd_csr(const float *d_out, int64_t n_sites, int C, const int32_t *start,
+                                    const int32_t *count, const int32_t *rows, const int32_t *first_row,
+                                    const int32_t *last_row, int mode, float *d_feats, int64_t ldf, void *stream) {
+  if (check_mode(mode)) return 1;
+  if (n_sites * C <= 0) return 0;
+  const bool vec = C % 4 == 0 && ldf % 4 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_feats)) & 15) == 0;
+  const int64_t total = n_sites * (vec ? C / 4 : C);
+  const unsigned blocks = (unsigned)min((int64_t)1 << 30, ceil_div(total, 256));   // one element group per thread
+  if (vec)
+    output_features_bwd_csr_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, n_sites, C, start, count, rows, first_row, last_row, mode, d_feats, ldf);
+  else
+    output_features_bwd_csr_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_out, n_sites, C, start, count, rows, first_row, last_row, mode, d_feats, ldf);
+  SCN_CHECK_LAUNCH("output_features_bwd_csr");
   count_launch(1);
   return 0;
 }

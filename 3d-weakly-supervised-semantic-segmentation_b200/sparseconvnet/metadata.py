@@ -118,6 +118,7 @@ class Metadata:
         self.mode = 4
         self.pv = self.count = self.first_row = self.last_row = None
         self.syncs = 0     # host synchronisations this forward (diagnostic)
+        self._site_rows = None
 
     # ------------------------------------------------------------------ InputLayer
     def build_input(self, coords, spatial_size, mode, device):
@@ -184,6 +185,20 @@ class Metadata:
         self.pv, self.count = self.pv[:P], self.count[:n0]
         self.first_row, self.last_row = self.first_row[:n0], self.last_row[:n0]
         return self.levels[sizes[0]]
+
+    def site_rows(self):
+        """(start, rows): input rows grouped by level-0 site, for the atomic-free OutputLayer backward."""
+        if self._site_rows is None:
+            n0 = self.count.shape[0]
+            dev = self.pv.device
+            start = alloc_flat(max(n0, 1), dev, torch.int32)
+            rows = alloc_flat(max(self.P, 1), dev, torch.int32)
+            nb = lib.b200scn_site_rows_scratch_bytes(n0)
+            scratch = alloc_flat(nb, dev, torch.uint8)
+            check(lib.b200scn_site_rows(ptr(self.pv), self.P, ptr(self.count), n0, ptr(start), ptr(rows), ptr(scratch),
+                                        nb, _lib.stream_for(self.pv)))
+            self._site_rows = (start, rows)
+        return self._site_rows
 
     # ------------------------------------------------------------------ strided levels on demand
     def get_down(self, size, s):

@@ -364,7 +364,9 @@ class OutputFeaturesFn(torch.autograd.Function):
         md = ctx.md
         g = g.contiguous()
         C = g.shape[1]
-        d = alloc_rows(ctx.n, C, g.device, zero=True)
-        check(lib.b200scn_output_features_bwd(ptr(g), md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
-                                              md.mode, ptr(d), C, _lib.stream_for(g)))
+        d = alloc_rows(ctx.n, C, g.device)
+        start, rows = md.site_rows()
+        check(lib.b200scn_output_features_bwd_csr(ptr(g), ctx.n, C, ptr(start), ptr(md.count), ptr(rows),
+                                                  ptr(md.first_row), ptr(md.last_row), md.mode, ptr(d), C,
+                                                  _lib.stream_for(g)))
         return d, None

@@ -142,6 +142,15 @@ int b200scn_output_features_bwd(const float *d_out, int64_t P, int C, const int3
                                 const int32_t *first_row, const int32_t *last_row, int mode,
                                 float *d_feats, int64_t ldf, void *stream);
 
+/* Rows grouped by site (counting sort over pv): start[v] (exclusive scan of count), rows[start[v]..+count[v]).
+ * With it the OutputLayer backward is a gather (each d_out row read once, no atomics). */
+size_t b200scn_site_rows_scratch_bytes(int64_t n_sites);
+int b200scn_site_rows(const int32_t *pv, int64_t P, const int32_t *count, int64_t n_sites, int32_t *start,
+                      int32_t *rows, void *scratch, size_t scratch_bytes, void *stream);
+int b200scn_output_features_bwd_csr(const float *d_out, int64_t n_sites, int C, const int32_t *start,
+                                    const int32_t *count, const int32_t *rows, const int32_t *first_row,
+                                    const int32_t *last_row, int mode, float *d_feats, int64_t ldf, void *stream);
+
 /* ------------------------------------------------------------------ point2mask (A12) */
 /* ops/point2mask/_ext_src/src/ball_query.cpp:8-33 (+ ball_query_gpu.cu:9-45). idx is fully written
  * (-1 sentinel included). */
