@@ -108,14 +108,27 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
   const int row0 = blockIdx.x * ROWS;
   const int nsplit = gridDim.y, split = blockIdx.y;
 
-  for (int k = tid; k < K; k += NTHREADS) kflag[k] = 0;
+  // The tile's slice of the map is one contiguous run of ROWS*K ints.  Full tiles copy it with 16-byte cp.async, all
+  // in flight at once (a dependent load->store loop with a division per element cost ~15 % of the tile, measured with a
+  // clock64 timeline of one CTA); the ragged last tile takes the scalar path.
+  {
+    const int live = min(ROWS, n_rows - row0) * K;   // entries that belong to real rows
+    const int32_t *msrc = map ? map + (int64_t)row0 * K : nullptr;
+    if (msrc && live == ROWS * K && ((ROWS * K) & 3) == 0 && (reinterpret_cast<uintptr_t>(msrc) & 15) == 0) {
+      for (int e = tid * 4; e < ROWS * K; e += NTHREADS * 4) cp_async16(smem_u32(smap + e), msrc + e, 16u);
+      cp_async_wait_all();
+    } else {
+      for (int e = tid; e < ROWS * K; e += NTHREADS)
+        smap[e] = e < live ? (msrc ? __ldg(msrc + e) : row0 + e) : -1;
+    }
+  }
   __syncthreads();
-  for (int e = tid; e < ROWS * K; e += NTHREADS) {
-    int r = e / K, k = e - r * K;
-    int v = -1;
-    if (row0 + r < n_rows) v = map ? __ldg(map + (int64_t)(row0 + r) * K + k) : row0 + r;
-    smap[e] = v;
-    if (v >= 0) kflag[k] = 1;
+  // offset k is present in this tile if any of its ROWS entries is: one warp-strided pass per offset
+  for (int k = warp; k < K; k += NTHREADS / 32) {
+    int any = 0;
+    for (int r = lane; r < ROWS; r += 32) any |= (smap[r * K + k] >= 0);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) kflag[k] = any;
   }
   __syncthreads();
   if (tid == 0) {
@@ -160,6 +173,16 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
       // touched only when it receives data or when stale data must be cleared -- at 2 cm voxels 60-80 % of the
       // (row, offset) slots are absent and stay untouched.
       uint32_t dirty = 0xFFFFFFFFu;    // unknown contents on first use
+      // per-lane constants of the tile (the producers are bound by their own issue chain, so keep the loop lean)
+      uint32_t soff[NI];               // swizzled byte offset of this lane's chunk in each of its rows
+      const int *mrow[NI];             // this lane's rows of the map slice
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int r = rbase + rl + 4 * i;
+        soff[i] = sw128(r, c);
+        mrow[i] = smap + r * K;
+      }
+      const int64_t lda4 = lda;
       for (int it = my_stage; it < T; it += nstages) {
         const int s = my_stage;
         const uint32_t ph = (uint32_t)(it / nstages) & 1u;
@@ -173,13 +196,14 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
         }
         if (chan < Cin) {
           const float *acol = A + chan;
+          int idx[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) idx[i] = mrow[i][k];   // all map reads first, then the copies
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
-            const int r = rbase + rl + 4 * i;
-            const int idx = smap[r * K + k];
-            const bool valid = idx >= 0;
+            const bool valid = idx[i] >= 0;
             if (valid || ((dirty >> i) & 1u))
-              cp_async16(a_st + sw128(r, c), valid ? (const void *)(acol + (int64_t)idx * lda) : (const void *)A,
+              cp_async16(a_st + soff[i], valid ? (const void *)(acol + (int64_t)idx[i] * lda4) : (const void *)A,
                          valid ? 16u : 0u);
             dirty = valid ? (dirty | (1u << i)) : (dirty & ~(1u << i));
           }
@@ -193,22 +217,30 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
     }
   } else if (lane == 0) {
     // ------------------------------------------------------------ MMA issuer (one thread)
+    // Descriptors differ only in the 14-bit start-address field: build the constant part once and patch the low word
+    // with 32-bit adds (this single thread's dependent instruction chain is on the consumer's critical path).
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull);
+    int s = 0, kb = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < T; ++it) {
-      const int s = it % nstages;
-      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(full + s, ph);
       tc_fence_after();
-      const int kb = it % nkb;
-      const int kvalid = min(32, Cin - kb * 32);
-      const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
+      const int nj = min(32, Cin - kb * 32) >> 3;
+      const uint32_t a_lo = desc_lo0 + ((a_base + (uint32_t)s * a_bytes) >> 4);
+      const uint32_t b_lo = desc_lo0 + ((b_base + (uint32_t)s * b_bytes) >> 4);
 #pragma unroll
-      for (int m = 0; m < MSUB; ++m)
-        for (int j = 0; j < (kvalid >> 3); ++j) {
-          const uint64_t ad = make_smem_desc(a_st + (uint32_t)m * (128 * 128) + j * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(b_st + j * 32, 16, 1024);
-          mma_tf32(tmem + (uint32_t)(m * Cout), ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+      for (int m = 0; m < MSUB; ++m) {
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
+          const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)m * (128 * 128 / 16) + 2 * j);
+          const uint64_t bd = desc_hi | (uint64_t)(b_lo + 2 * j);
+          mma_tf32(tmem + (uint32_t)(m * Cout), ad, bd, idesc, (it | j) ? 1u : 0u);
         }
+      }
       mma_commit(empty + s);
+      if (++kb == nkb) kb = 0;
+      if (++s == nstages) { s = 0; ph ^= 1u; }
     }
     mma_commit(accum);
   }
