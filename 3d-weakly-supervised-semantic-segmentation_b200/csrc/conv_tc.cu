@@ -391,7 +391,7 @@ static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, 
 namespace b200scn {
 
 constexpr int kDwPairs = 32;  // pairs per stage (4 MMAs of K = 8)
-constexpr int kDwWarps = 8;   // producer warps, two per stage
+constexpr int kDwWarps = 16;  // producer warps, four per stage
 
 // A stage holds only the VALID 32-channel blocks of A (ab of them) followed by the gb blocks of G.  The M = 128 MMA of
 // tile t still reads four MN blocks starting at block 4t; blocks past Ca alias whatever follows in shared memory
@@ -448,18 +448,40 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
     const int c = lane & 7, rl = lane >> 3;
     const int my_stage = warp % nstages, part = warp / nstages;
     const int rows_per_warp = kDwPairs / wps;
+    // the pair indices of the NEXT iteration are fetched while the current one is being staged (the index load ->
+    // address -> copy chain is otherwise a serial global round trip at the head of every stage)
+    constexpr int kMaxSlots = kDwPairs / 4 / 2;   // slots per lane at the smallest warps-per-stage (2)
+    int nra[kMaxSlots], nrg[kMaxSlots];
+    const int nslots = rows_per_warp / 4;
+    auto fetch = [&](int it_) {
+      const int pb = p0 + it_ * kDwPairs;
+#pragma unroll
+      for (int i = 0; i < kMaxSlots; ++i) {
+        if (i < nslots) {
+          const int p = pb + part * rows_per_warp + rl + 4 * i;
+          const bool live = it_ < T && p < p1;
+          nra[i] = live ? (pair_a ? __ldg(pair_a + p) : p) : -1;
+          nrg[i] = live ? (pair_g ? __ldg(pair_g + p) : p) : -1;
+        }
+      }
+    };
+    fetch(my_stage);
     for (int it = my_stage; it < T; it += nstages) {
       const int s = my_stage;
       const uint32_t ph = (uint32_t)(it / nstages) & 1u;
+      int cra[kMaxSlots], crg[kMaxSlots];
+#pragma unroll
+      for (int i = 0; i < kMaxSlots; ++i) { cra[i] = nra[i]; crg[i] = nrg[i]; }
+      fetch(it + nstages);
       mbar_wait(empty + s, ph ^ 1u);
       const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
-      const int pbase = p0 + it * kDwPairs;
-      for (int i = 0; i < rows_per_warp / 4; ++i) {
+#pragma unroll
+      for (int i = 0; i < kMaxSlots; ++i) {
+        if (i >= nslots) break;
         const int r = part * rows_per_warp + rl + 4 * i;
-        const int p = pbase + r;
-        const bool live = p < p1;
-        const int ra = live ? (pair_a ? __ldg(pair_a + p) : p) : 0;
-        const int rg = live ? (pair_g ? __ldg(pair_g + p) : p) : 0;
+        const bool live = cra[i] >= 0;
+        const int ra = live ? cra[i] : 0;
+        const int rg = live ? crg[i] : 0;
         const float *arow = A + (int64_t)ra * lda + c * 4;
         const float *grow = G + (int64_t)rg * ldg + c * 4;
         const uint32_t off = sw128_32b(r, c);
@@ -477,19 +499,26 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
       mbar_arrive(full + s);
     }
   } else if (lane == 0) {
+    // constant descriptor part once, 32-bit patching of the start address per MMA (see the gather kernel)
+    const uint64_t desc_hi = make_smem_desc(0, blk, 512, 1) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)(make_smem_desc(0, blk, 512, 1) & 0xFFFFFFFFull);
+    int s = 0;
+    uint32_t ph = 0;
     for (int it = 0; it < T; ++it) {
-      const int s = it % nstages;
-      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       mbar_wait(full + s, ph);
       tc_fence_after();
-      const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
-      for (int t = 0; t < mt; ++t)
+      const uint32_t a_lo = desc_lo0 + ((base + (uint32_t)s * stage_bytes) >> 4);
+      const uint32_t g_lo = a_lo + (a_bytes >> 4);
+      for (int t = 0; t < mt; ++t) {
+#pragma unroll
         for (int j = 0; j < kDwPairs / 8; ++j) {
-          const uint64_t ad = make_smem_desc(a_st + (uint32_t)(4 * t) * blk + j * 1024, blk, 512, 1);
-          const uint64_t gd = make_smem_desc(g_st + j * 1024, blk, 512, 1);
-          mma_tf32(tmem + (uint32_t)(t * Cg), ad, gd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+          const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)(4 * t) * (blk >> 4) + j * 64);
+          const uint64_t gd = desc_hi | (uint64_t)(g_lo + j * 64);
+          mma_tf32(tmem + (uint32_t)(t * Cg), ad, gd, idesc, (it | j) ? 1u : 0u);
         }
+      }
       mma_commit(empty + s);
+      if (++s == nstages) { s = 0; ph ^= 1u; }
     }
     mma_commit(accum);
   }
