@@ -367,12 +367,25 @@ pair_dw_smallca_kernel(const float *__restrict__ A, int64_t lda, const float *__
     float acc[CA];
 #pragma unroll
     for (int j = 0; j < CA; ++j) acc[j] = 0.f;
-    for (int p = p0 + warp; p < p1; p += nw) {
-      const int ra = pair_a ? __ldg(pair_a + p) : p;
-      const int rg = pair_g ? __ldg(pair_g + p) : p;
-      const float g = cg < Cg ? __ldg(G + (int64_t)rg * ldg + cg) : 0.f;
+    for (int pb = p0 + warp * 4; pb < p1; pb += nw * 4) {   // four pairs per trip: index loads, then data loads, then FMAs
+      int ra[4], rg[4];
 #pragma unroll
-      for (int j = 0; j < CA; ++j) acc[j] = fmaf(__ldg(A + (int64_t)ra * lda + j), g, acc[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int p = pb + u;
+        ra[u] = p < p1 ? (pair_a ? __ldg(pair_a + p) : p) : -1;
+        rg[u] = p < p1 ? (pair_g ? __ldg(pair_g + p) : p) : 0;
+      }
+      float g[4], a[4][CA];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        g[u] = (ra[u] >= 0 && cg < Cg) ? __ldg(G + (int64_t)rg[u] * ldg + cg) : 0.f;
+#pragma unroll
+        for (int j = 0; j < CA; ++j) a[u][j] = ra[u] >= 0 ? __ldg(A + (int64_t)ra[u] * lda + j) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < CA; ++j) acc[j] = fmaf(a[u][j], g[u], acc[j]);
     }
     if (cg < Cg) {
 #pragma unroll
