@@ -50,6 +50,7 @@ bn_reduce_kernel(const float *__restrict__ x, int64_t ldx, const float *__restri
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(r0 + rows_per_block, n);
   if (active) {
+#pragma unroll 4
     for (int64_t r = r0 + rg; r < r1; r += rps) {
       float xv[VEC], gv[VEC];
       if (VEC == 4) {
@@ -114,31 +115,36 @@ __global__ void bn_eval_stats_kernel(int C, const float *running_mean, const flo
   save_invstd[c] = rsqrtf(running_var[c] + eps);
 }
 
+// y = leaky_relu(bn(x)): thread (tx, ty) owns VEC channels of rows ty, ty + rps, ... of its block's slab, so the
+// per-channel constants live in registers and there is no index arithmetic beyond one add per row
 template <int VEC>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float *__restrict__ x, int64_t ldx, int64_t n, int C, const float *__restrict__ mean,
-                const float *__restrict__ invstd, const float *__restrict__ weight,
-                const float *__restrict__ bias, float leak, float *__restrict__ y, int64_t ldy) {
-  const int cv = C / VEC;
-  const int64_t total = n * cv;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = t / cv;
-    int c0 = (int)(t - r * cv) * VEC;
+bn_apply_kernel(const float *__restrict__ x, int64_t ldx, int64_t n, int C, int tpr, int rps,
+                int64_t rows_per_block, const float *__restrict__ mean, const float *__restrict__ invstd,
+                const float *__restrict__ weight, const float *__restrict__ bias, float leak,
+                float *__restrict__ y, int64_t ldy) {
+  const int tid = threadIdx.x;
+  const int rg = tid / tpr, c0 = (tid - rg * tpr) * VEC;
+  if (rg >= rps || c0 >= C) return;
+  float m[VEC], is[VEC], w[VEC], b[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    m[v] = __ldg(mean + c0 + v); is[v] = __ldg(invstd + c0 + v); w[v] = __ldg(weight + c0 + v); b[v] = __ldg(bias + c0 + v);
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, n);
+#pragma unroll 4
+  for (int64_t r = r0 + rg; r < r1; r += rps) {
     if (VEC == 4) {
-      float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
-      float4 mm = __ldg(reinterpret_cast<const float4 *>(mean + c0));
-      float4 ii = __ldg(reinterpret_cast<const float4 *>(invstd + c0));
-      float4 ww = __ldg(reinterpret_cast<const float4 *>(weight + c0));
-      float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + c0));
+      float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
       float4 o;
-      o.x = bn_affine(v.x, mm.x, ii.x, ww.x, bb.x); o.x = o.x > 0.f ? o.x : leak * o.x;
-      o.y = bn_affine(v.y, mm.y, ii.y, ww.y, bb.y); o.y = o.y > 0.f ? o.y : leak * o.y;
-      o.z = bn_affine(v.z, mm.z, ii.z, ww.z, bb.z); o.z = o.z > 0.f ? o.z : leak * o.z;
-      o.w = bn_affine(v.w, mm.w, ii.w, ww.w, bb.w); o.w = o.w > 0.f ? o.w : leak * o.w;
+      o.x = bn_affine(t.x, m[0], is[0], w[0], b[0]); o.x = o.x > 0.f ? o.x : leak * o.x;
+      o.y = bn_affine(t.y, m[1], is[1], w[1], b[1]); o.y = o.y > 0.f ? o.y : leak * o.y;
+      o.z = bn_affine(t.z, m[2], is[2], w[2], b[2]); o.z = o.z > 0.f ? o.z : leak * o.z;
+      o.w = bn_affine(t.w, m[3], is[3], w[3], b[3]); o.w = o.w > 0.f ? o.w : leak * o.w;
       *reinterpret_cast<float4 *>(y + r * ldy + c0) = o;
     } else {
-      float o = bn_affine(__ldg(x + r * ldx + c0), mean[c0], invstd[c0], weight[c0], bias[c0]);
+      float o = bn_affine(__ldg(x + r * ldx + c0), m[0], is[0], w[0], b[0]);
       y[r * ldy + c0] = o > 0.f ? o : leak * o;
     }
   }
@@ -155,16 +161,27 @@ __global__ void bn_finalize_bwd_kernel(const double *__restrict__ sums, int C,
 template <int VEC>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ dy, int64_t lddy,
-                    int64_t n, int C, const float *__restrict__ mean, const float *__restrict__ invstd,
-                    const float *__restrict__ weight, const float *__restrict__ bias, float leak,
-                    const double *__restrict__ sums, float *__restrict__ dx, int64_t lddx) {
-  const int cv = C / VEC;
-  const int64_t total = n * cv;
+                    int64_t n, int C, int tpr, int rps, int64_t rows_per_block, const float *__restrict__ mean,
+                    const float *__restrict__ invstd, const float *__restrict__ weight,
+                    const float *__restrict__ bias, float leak, const double *__restrict__ sums,
+                    float *__restrict__ dx, int64_t lddx) {
+  const int tid = threadIdx.x;
+  const int rg = tid / tpr, c0 = (tid - rg * tpr) * VEC;
+  if (rg >= rps || c0 >= C) return;
   const float inv_n = 1.f / (float)n;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = t / cv;
-    int c0 = (int)(t - r * cv) * VEC;
+  float m[VEC], is[VEC], w[VEC], b[VEC], k0[VEC], k1[VEC], sc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int c = c0 + v;
+    m[v] = __ldg(mean + c); is[v] = __ldg(invstd + c); w[v] = __ldg(weight + c); b[v] = __ldg(bias + c);
+    k0[v] = (float)sums[c] * inv_n;                         // mean of g
+    k1[v] = (float)sums[C + c] * is[v] * is[v] * inv_n;      // dotp * invstd^2 / n
+    sc[v] = is[v] * w[v];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, n);
+#pragma unroll 2
+  for (int64_t r = r0 + rg; r < r1; r += rps) {
     float xv[VEC], gv[VEC], ov[VEC];
     if (VEC == 4) {
       float4 a = __ldg(reinterpret_cast<const float4 *>(x + r * ldx + c0));
@@ -177,12 +194,9 @@ bn_bwd_apply_kernel(const float *__restrict__ x, int64_t ldx, const float *__res
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      int c = c0 + v;
-      float m = __ldg(mean + c), is = __ldg(invstd + c), w = __ldg(weight + c), b = __ldg(bias + c);
-      float yv = bn_affine(xv[v], m, is, w, b);
-      float g = yv > 0.f ? gv[v] : leak * gv[v];
-      float sg = (float)sums[c], dot = (float)sums[C + c];
-      ov[v] = (g - sg * inv_n - (xv[v] - m) * dot * is * is * inv_n) * is * w;
+      const float yv = bn_affine(xv[v], m[v], is[v], w[v], b[v]);
+      const float g = yv > 0.f ? gv[v] : leak * gv[v];
+      ov[v] = (g - k0[v] - (xv[v] - m[v]) * k1[v]) * sc[v];
     }
     if (VEC == 4) *reinterpret_cast<float4 *>(dx + r * lddx + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
     else dx[r * lddx + c0] = ov[0];
@@ -199,9 +213,10 @@ static int launch_reduce(const float *x, int64_t ldx, const float *dy, int64_t l
                          float leak, double *sums, bool vec, cudaStream_t st) {
   BnCfg cfg = bn_cfg(C, vec ? 4 : 1);
   if (cfg.tpr > 256) return set_error("batchnorm: %d planes unsupported on this path", C);
+  // few enough CTAs that the 2*C double atomics per CTA do not pile up on the same addresses at small n
   int64_t blocks = kNumSMs * 4;
   int64_t rows_per_block = ceil_div(n, blocks);
-  if (rows_per_block < cfg.rps) rows_per_block = cfg.rps;
+  if (rows_per_block < (int64_t)cfg.rps * 16) rows_per_block = (int64_t)cfg.rps * 16;
   blocks = ceil_div(n, rows_per_block);
   size_t smem = sizeof(float) * 2 * (size_t)cfg.rps * C;
   if (smem > 48 * 1024) return set_error("batchnorm: shared memory %zu too large", smem);
@@ -237,10 +252,14 @@ int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const floa
     bn_eval_stats_kernel<<<cb, 128, 0, st>>>(C, running_mean, running_var, eps, save_mean, save_invstd);
   }
   if (n > 0) {
-    int64_t total = n * (vec ? C / 4 : C);
-    unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(total, 256));
-    if (vec) bn_apply_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, n, C, save_mean, save_invstd, weight, bias, leak, y, ldy);
-    else bn_apply_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, n, C, save_mean, save_invstd, weight, bias, leak, y, ldy);
+    BnCfg cfg = bn_cfg(C, vec ? 4 : 1);
+    if (cfg.tpr > 256) return set_error("batchnorm: %d planes unsupported on this path", C);
+    int64_t blocks = kNumSMs * 8;
+    int64_t rows_per_block = ceil_div(n, blocks);
+    if (rows_per_block < cfg.rps) rows_per_block = cfg.rps;
+    blocks = ceil_div(n, rows_per_block);
+    if (vec) bn_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, y, ldy);
+    else bn_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, y, ldy);
   }
   SCN_CHECK_LAUNCH("bn_forward");
   count_launch(n > 0 ? 2 : 1);
@@ -257,10 +276,14 @@ int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t ld
   if (n > 0 && launch_reduce<1>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, vec, st)) return 1;
   bn_finalize_bwd_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(scratch, C, save_invstd, d_weight, d_bias);
   if (n > 0) {
-    int64_t total = n * (vec ? C / 4 : C);
-    unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(total, 256));
-    if (vec) bn_bwd_apply_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
-    else bn_bwd_apply_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
+    BnCfg cfg = bn_cfg(C, vec ? 4 : 1);
+    if (cfg.tpr > 256) return set_error("batchnorm: %d planes unsupported on this path", C);
+    int64_t blocks = kNumSMs * 8;
+    int64_t rows_per_block = ceil_div(n, blocks);
+    if (rows_per_block < cfg.rps) rows_per_block = cfg.rps;
+    blocks = ceil_div(n, rows_per_block);
+    if (vec) bn_bwd_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
+    else bn_bwd_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, scratch, dx, lddx);
   }
   SCN_CHECK_LAUNCH("bn_backward");
   count_launch(n > 0 ? 2 : 1);
