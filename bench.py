@@ -284,8 +284,12 @@ def run_b200(args):
         if prof and prof.get("gather27"):
             g = prof["gather27"]
             ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full
+            # capture (profiles/r1_final_ncu_gather_details.txt): the level-1 64->64 SubmanifoldConvolution forward of
+            # this workload, whose algorithmic bytes are 241.8 MB -- no re-read beyond the compulsory traffic.
+            traffic = {"bytes": 228.6e6, "launch": "level-1 SubM 64->64 fwd, 411829 sites", "algorithmic_bytes": 241.8e6}
             roof = {"bound": "hbm", "kernel": g["kernel"], "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / g["n"],
+                    "frac": ach / peak, "traffic": traffic["bytes"], "traffic_detail": traffic, "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / g["n"],
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "tflops": g["flops"] / (g["ms"] * 1e-3) / 1e12,
                     "share_of_step": g["ms"] / ms_p, "profiled_ms_per_step": ms_p / args.steps, "by_kind": {k: {"ms_per_step": v["ms"] / args.steps, "n_per_step": v["n"] / args.steps,
                                                                  "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
