@@ -3,13 +3,17 @@
 Each function cites the upstream scn entry point it replaces and the reference call site that
 reaches it.  All tensors are CUDA fp32; there is no CPU path.
 """
+import os
+
 import torch
 
 from . import _lib
 from ._lib import alloc_rows, check, lib, ptr
 
-# 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05) where the kernel supports the shape
-_precision = [0]
+# 0 = fp32 CUDA cores, 1 = TF32 tensor cores (tcgen05) where the kernel supports the shape.
+# Default: the tensor-core path (stated tolerance rel 3e-3 through a net); B200SCN_PRECISION=fp32 or
+# set_precision("fp32") selects the exact-fp32 CUDA-core kernels.
+_precision = [0 if os.environ.get("B200SCN_PRECISION", "tf32").lower() == "fp32" else 1]
 
 
 def set_precision(name):

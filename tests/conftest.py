@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# tests compare against the fp32 oracle at tight tolerances unless they pick the TF32 path themselves
+os.environ.setdefault("B200SCN_PRECISION", "fp32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "3d-weakly-supervised-semantic-segmentation_b200")
 for p in (ROOT, PKG):
