@@ -80,14 +80,14 @@ static TcSmemLayout tc_layout(int msub, int Cout, int K, int nstages) {
 // NPW producer warps, NPW/4 per stage, each gathering an equal share of the stage's rows and weight rows
 // (the producers are bound by their own dependent issue chain, so 16 warps beat 4 by ~3x: profiles/).
 template <uint32_t NT, int MSUB, int NPW>
-__global__ void __launch_bounds__(32 * (NPW + 1))
+__global__ void __launch_bounds__(32 * (NPW + 2))
 gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
                       const int32_t *__restrict__ map, int n_rows, int K, int Cin, int Cout,
                       const float *__restrict__ addend,
                       int64_t ldadd, float *__restrict__ out, int64_t ldo, int nstages, uint32_t idesc,
                       uint32_t map_off, uint32_t klist_off, uint32_t bar_off, int w_rows_per_k, int w_row0) {
   constexpr int ROWS = MSUB * 128;
-  constexpr int NTHREADS = 32 * (NPW + 1);
+  constexpr int NTHREADS = 32 * (NPW + 2);   // producers, MMA-issuing warp, weight-TMA warp
   constexpr int WPS = NPW / 4;  // producer warps per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -190,10 +190,6 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
         const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
         const int chan = kb * 32 + c * 4;
         const uint32_t a_st = a_base + (uint32_t)s * a_bytes, b_st = b_base + (uint32_t)s * b_bytes;
-        if (half == 0 && lane == 0) {   // weight slice W[k][:, kb*32 .. +32): one tiled TMA load, counted in bytes
-          mbar_arrive_expect_tx(full + s, b_bytes);
-          tma_load_2d(b_st, &tmW, kb * 32, k * w_rows_per_k + w_row0, full + s);
-        }
         if (chan < Cin) {
           const float *acol = A + chan;
           int idx[NI];
@@ -213,6 +209,21 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
         cp_async_wait_all();
         fence_proxy_async();
         mbar_arrive(full + s);
+      }
+    }
+  } else if (warp == NPW + 1) {
+    // ------------------------------------------------------------ weight TMA (one thread of its own warp)
+    // W[k][:, kb*32 .. +32) per stage: one tiled TMA load, counted in bytes on the stage's "full" barrier.  Kept off
+    // the gathering warps: the arrive.expect_tx + TMA issue sat on the critical path of the stage's slowest producer.
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < T; ++it) {
+        mbar_wait_sleep(empty + s, ph ^ 1u, 500);
+        const int k = klist[it / nkb], kb = it - (it / nkb) * nkb;
+        mbar_arrive_expect_tx(full + s, b_bytes);
+        tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, k * w_rows_per_k + w_row0, full + s);
+        if (++s == nstages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (lane == 0) {
@@ -309,7 +320,7 @@ static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (K*Cout_total, Cin) K-major stack
   if (make_tmap(&tmW, Wkm, (int64_t)K * w_rows_per_k, Cin, Cin, Cout)) return 1;
-  kern<<<grid, 32 * (NPW + 1), L.total, st>>>(tmW, A, lda, map, (int)n_out, K, Cin, Cout, addend, ldadd, out, ldo,
+  kern<<<grid, 32 * (NPW + 2), L.total, st>>>(tmW, A, lda, map, (int)n_out, K, Cin, Cout, addend, ldadd, out, ldo,
                                               nstages, idesc, L.map_off, L.klist_off, L.bar_off, w_rows_per_k, w_row0);
   return 0;
 }
