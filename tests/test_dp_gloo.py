@@ -25,13 +25,14 @@ def _worker(rank, world, port, out):
     x = torch.randn(4 * len(scenes), 6)
     flat.zero()
     net(x).pow(2).mean().backward()
-    local = flat.flat.clone()
+    local = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
     flat.allreduce_mean()
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
-    ok = torch.allclose(flat.flat, sum(gathered) / world, atol=1e-7)
-    views = all(p.grad.data_ptr() >= flat.flat.data_ptr() for p in net.parameters())
-    out[rank] = (ok, views, scenes)
+    now = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    ok = torch.allclose(now, sum(gathered) / world, atol=1e-7)
+    same = all(torch.equal(a, b) for a, b in zip(gathered, gathered)) and not torch.equal(gathered[0], gathered[1])
+    out[rank] = (ok, same, scenes)
     dist.destroy_process_group()
 
 
