@@ -1,0 +1,489 @@
+// conv_halo.cu -- submanifold 3x3x3 convolution over SPATIALLY ORDERED tiles with the tile's input rows staged once in
+// shared memory ("halo"), TF32 tcgen05 contraction (replaces upstream scn's
+// dConvolution_KMxKN_forwardA/B x 27 launches behind SubmanifoldConvolution_updateOutput / _backward).
+//
+// Why: the output-stationary gather kernel (conv_tc.cu) fetches every (row, offset) pair from L2 separately -- 538 /
+// 1190 / 1650 gathered rows per 128-row tile at levels 0 / 1 / 2 of the 2 cm benchmark -- and is bound by the L2 round
+// trip of every pipeline stage.  A tile of 128 sites that are neighbours in space only references 170 / 223 / 255
+// DISTINCT input rows (measured on the benchmark scenes).  So:
+//   plan (once per level and step):  sites sorted along a Morton curve (perm), cut into 128-row tiles; per tile the set
+//        of distinct neighbour ids ("halo", <= hcap slots) and a local map lmap[k][r] = halo slot of nbr[perm[r]][k];
+//   conv (every layer, fwd and bwd-input): per 32-channel block the tile's halo rows are copied global -> shared ONCE
+//        (cp.async, the only L2 latency left), then the 27 per-offset A operands are assembled shared -> shared into the
+//        SWIZZLE_128B stage images tcgen05.mma reads; W slices by TMA; accumulator in TMEM; each output row written once.
+// Slots beyond hcap (0xFFFE in lmap) are fetched from global through the ordinary neighbour map, so any input is handled.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200scn {
+
+using namespace tc;
+
+int make_weight_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows);  // conv_tc.cu
+
+constexpr int kTile = 128;            // output rows per tile (= tcgen05 M)
+constexpr int kTileMap = 27 * kTile;  // lmap entries per tile
+constexpr uint16_t kAbsent = 0xFFFF, kOverflow = 0xFFFE;
+
+// ------------------------------------------------------------------------------------------------ Morton keys
+__device__ __forceinline__ uint64_t spread3(uint64_t v) {   // 16 bits -> every third bit
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+__global__ void morton_keys_kernel(const uint64_t *__restrict__ ukeys, int64_t n, uint64_t *__restrict__ mk) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x, y, z, b;
+  split_key(ukeys[i], x, y, z, b);
+  mk[i] = ((uint64_t)b << 48) | (spread3((uint64_t)x) << 2) | (spread3((uint64_t)y) << 1) | spread3((uint64_t)z);
+}
+
+// ------------------------------------------------------------------------------------------------ tile plan
+constexpr int kPlanThreads = 256;
+constexpr int kPlanHash = 8192;   // >= 2 x the 27*128 ids a tile can reference
+
+__global__ void __launch_bounds__(kPlanThreads)
+tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ perm, int n, int hcap,
+                 uint16_t *__restrict__ lmap, int32_t *__restrict__ halo_ids, int32_t *__restrict__ halo_n,
+                 uint32_t *__restrict__ kmask) {
+  extern __shared__ int psm[];
+  int *ids = psm;                                               // [k][r]
+  int *hk = ids + kTileMap;                                     // hash keys (site ids)
+  unsigned short *hv = reinterpret_cast<unsigned short *>(hk + kPlanHash);   // halo slot of the key
+  __shared__ int cnt;
+  __shared__ unsigned km;
+  const int tid = threadIdx.x, tile = blockIdx.x, row0 = tile * kTile;
+  for (int i = tid; i < kPlanHash; i += kPlanThreads) hk[i] = -1;
+  if (tid == 0) { cnt = 0; km = 0; }
+  for (int e = tid; e < kTileMap; e += kPlanThreads) {   // global order (row, k): one contiguous 108-byte run per row
+    const int r = e / 27, k = e - r * 27, row = row0 + r;
+    int id = -1;
+    if (row < n) id = __ldg(nbr + (int64_t)__ldg(perm + row) * 27 + k);
+    ids[k * kTile + r] = id;
+  }
+  __syncthreads();
+  for (int e = tid; e < kTileMap; e += kPlanThreads) {   // whole warps: kTileMap and kPlanThreads are multiples of 32
+    const int id = ids[e];
+    if (id >= 0) {
+      uint32_t h = ((uint32_t)id * 2654435761u) >> 19;   // 13 bits
+      for (;;) {
+        const int prev = atomicCAS(hk + h, -1, id);
+        if (prev == -1) { hv[h] = (unsigned short)atomicAdd(&cnt, 1); break; }
+        if (prev == id) break;
+        h = (h + 1) & (kPlanHash - 1);
+      }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, id >= 0);
+    if ((tid & 31) == 0 && any) atomicOr(&km, 1u << (e / kTile));
+  }
+  __syncthreads();
+  uint16_t *lm = lmap + (int64_t)tile * kTileMap;
+  for (int e = tid; e < kTileMap; e += kPlanThreads) {
+    const int id = ids[e];
+    uint16_t v = kAbsent;
+    if (id >= 0) {
+      uint32_t h = ((uint32_t)id * 2654435761u) >> 19;
+      while (hk[h] != id) h = (h + 1) & (kPlanHash - 1);
+      const int slot = hv[h];
+      v = slot < hcap ? (uint16_t)slot : kOverflow;
+    }
+    lm[e] = v;
+  }
+  for (int i = tid; i < kPlanHash; i += kPlanThreads)
+    if (hk[i] >= 0 && hv[i] < hcap) halo_ids[(int64_t)tile * hcap + hv[i]] = hk[i];
+  if (tid == 0) {
+    halo_n[tile] = min(cnt, hcap);
+    kmask[tile] = km;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ convolution
+constexpr int kHaloWarps = 16;   // stage-building warps
+constexpr int kHaloMaxStages = 4;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+struct HaloSmem {
+  uint32_t a_off, b_off, halo_off, lmap_off, orow_off, hids_off, klist_off, bar_off, total;
+};
+
+constexpr int kHaloMaxW = 16;    // weight-ring slots
+
+static HaloSmem halo_layout(int nstages, int nw, int Cout, int hcap) {
+  HaloSmem L;
+  L.a_off = 0;
+  L.b_off = (uint32_t)nstages * kTile * 128;
+  L.halo_off = L.b_off + (uint32_t)nw * Cout * 128;
+  L.lmap_off = L.halo_off + (uint32_t)hcap * 128;
+  L.orow_off = L.lmap_off + ((kTileMap * 2 + 15) & ~15);
+  L.hids_off = L.orow_off + kTile * 4;
+  L.klist_off = L.hids_off + (((uint32_t)hcap * 4 + 15) & ~15u);
+  L.bar_off = L.klist_off + 128;
+  L.total = L.bar_off + 512 + 1024;   // + alignment slack
+  return L;
+}
+
+// Diagnostic: clock64 timeline of ONE CTA (b200scn_debug_timeline).  Slots: [0] start, [1] prologue done, [2] accumulator
+// seen by the epilogue, [3] epilogue done; builders of stage group g (lane 0 of its first warp): 64 + g*256 + 2*use + {0:
+// slot free, 1: built}, halo load of channel block kb: 32 + 2*kb + {0,1}; MMA thread: 1088 + 2*it + {0: operands seen, 1: issued}.
+__device__ long long *g_timeline = nullptr;
+__device__ int g_timeline_tile = -1;
+#define SCN_TL(slot) do { if (tl) tl[slot] = clock64(); } while (0)
+
+// NT: TMEM columns (power of two >= Cout); NSTAGES: 2 or 4 stage images, each built by 16 / NSTAGES warps.
+template <uint32_t NT, int NSTAGES>
+__global__ void __launch_bounds__(32 * (kHaloWarps + 2), NSTAGES == 2 ? 2 : 1)
+halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
+                    const int32_t *__restrict__ nbr, const int32_t *__restrict__ perm,
+                    const uint16_t *__restrict__ lmap, const int32_t *__restrict__ halo_ids,
+                    const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
+                    int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
+                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int w_rows_per_k, int w_row0) {
+  constexpr int NPW = kHaloWarps;
+  constexpr int NTHREADS = 32 * (NPW + 2);
+  constexpr int WPS = NPW / NSTAGES;   // warps per stage image
+  constexpr int RPW = kTile / WPS;     // rows per warp
+  constexpr int NI = RPW / 4;          // row slots per lane (8 lanes share a row)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t *sm = smem_raw + (base - raw);
+  const uint32_t a_bytes = kTile * 128, b_bytes = (uint32_t)Cout * 128;
+  const uint32_t a_base = base + L.a_off, b_base = base + L.b_off, halo_base = base + L.halo_off;
+  const uint16_t *slmap = reinterpret_cast<const uint16_t *>(sm + L.lmap_off);
+  int *sorow = reinterpret_cast<int *>(sm + L.orow_off);
+  int *shids = reinterpret_cast<int *>(sm + L.hids_off);
+  int *klist = reinterpret_cast<int *>(sm + L.klist_off);
+  int *nk_p = klist + 27;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + L.bar_off);
+  uint64_t *empty = full + kHaloMaxStages;
+  uint64_t *accum = empty + kHaloMaxStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
+  uint64_t *wfull = accum + 2;            // weight ring: its own, deeper pipeline (a W slice is a ~1 us TMA round trip
+  uint64_t *wempty = wfull + kHaloMaxW;   // that depends on nothing in the tile, so it is prefetched `nw` stages ahead)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tile = blockIdx.x, row0 = tile * kTile;
+  const int hn = __ldg(halo_n + tile);
+  long long *tl = (g_timeline && g_timeline_tile == tile && lane == 0) ? g_timeline : nullptr;
+  if (tid == 0) SCN_TL(0);
+
+  // ---- prologue: the tile's plan slice -> shared memory
+  {
+    const uint16_t *src = lmap + (int64_t)tile * kTileMap;   // 6912 bytes, 16-byte aligned
+    for (int e = tid; e < kTileMap * 2 / 16; e += NTHREADS) cp_async16(base + L.lmap_off + e * 16, src + e * 8, 16u);
+    if (tid < kTile) sorow[tid] = row0 + tid < n_rows ? __ldg(perm + row0 + tid) : -1;
+    for (int i = tid; i < hn; i += NTHREADS) shids[i] = __ldg(halo_ids + (int64_t)tile * hcap + i);
+    if (tid == 0) {
+      const uint32_t km = __ldg(kmask + tile);
+      int n = 0;
+      for (int k = 0; k < 27; ++k)
+        if ((km >> k) & 1u) klist[n++] = k;
+      *nk_p = n;
+      for (int s = 0; s < NSTAGES; ++s) {
+        mbar_init(full + s, 32 * WPS);   // every building lane
+        mbar_init(empty + s, 1);
+      }
+      for (int s = 0; s < nw; ++s) {
+        mbar_init(wfull + s, 1);             // the weight TMA's expect_tx arrival
+        mbar_init(wempty + s, 1);
+      }
+      mbar_init(accum, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tmW);
+    }
+    cp_async_wait_all();
+  }
+  if (warp == NPW) tmem_alloc<NT>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nk = *nk_p;
+  const int nkb = (Cin + 31) >> 5;
+  if (tid == 0) SCN_TL(1);
+  const int T = nk * nkb;   // stage (kb, ki) has index it = kb * nk + ki: channel blocks outermost
+
+  if (warp < NPW) {
+    // ------------------------------------------------------------ halo loaders + stage builders
+    const int c = lane & 7, rl = lane >> 3;
+    const int my_stage = warp % NSTAGES, part = warp / NSTAGES;
+    const int rbase = part * RPW;
+    uint32_t soff[NI];   // swizzled byte offset of this lane's chunk in each of its rows
+    int rws[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      rws[i] = rbase + rl + 4 * i;
+      soff[i] = sw128(rws[i], c);
+    }
+    // `dirty`: which of this lane's row slots of its stage image hold data (the warp owns the same rows of the same
+    // image for the whole tile), so absent neighbours cost a zero store only where stale data must be cleared
+    uint32_t dirty = 0xFFFFFFFFu;
+    const uint32_t a_st = a_base + (uint32_t)my_stage * a_bytes;
+    int it = my_stage;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int chan = kb * 32 + c * 4;
+      named_bar_sync(1, 32 * NPW);   // every builder has finished reading the previous channel block's halo
+      if (tid == 0) SCN_TL(32 + 2 * kb);
+      if (chan < Cin) {
+        const float *acol = A + chan;
+        for (int h = tid >> 3; h < hn; h += 4 * NPW)
+          cp_async16(halo_base + (uint32_t)h * 128 + c * 16, acol + (int64_t)shids[h] * lda, 16u);
+      }
+      cp_async_wait_all();
+      named_bar_sync(1, 32 * NPW);   // halo complete and visible to all builders
+      if (tid == 0) SCN_TL(33 + 2 * kb);
+      const int it_end = (kb + 1) * nk;
+      for (; it < it_end; it += NSTAGES) {
+        const uint32_t ph = (uint32_t)(it / NSTAGES) & 1u;
+        mbar_wait_sleep(empty + my_stage, ph ^ 1u, 200);
+        if (part == 0 && it / NSTAGES < 128) SCN_TL(64 + my_stage * 256 + 2 * (it / NSTAGES));
+        const int k = klist[it - kb * nk];
+        if (chan < Cin) {
+          uint32_t slot[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) slot[i] = slmap[k * kTile + rws[i]];   // all map reads first
+          float4 v[NI];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            if (slot[i] < kOverflow) {
+              v[i] = lds_f4(halo_base + slot[i] * 128 + c * 16);
+            } else if (slot[i] == kOverflow) {   // beyond the halo capacity: through the global neighbour map
+              const int idx = __ldg(nbr + (int64_t)sorow[rws[i]] * 27 + k);
+              v[i] = ldg_f4(A + (int64_t)idx * lda + chan);
+            } else {
+              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const bool present = slot[i] != kAbsent;
+            if (present || ((dirty >> i) & 1u)) sts_f4(a_st + soff[i], v[i]);
+            dirty = present ? (dirty | (1u << i)) : (dirty & ~(1u << i));
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(full + my_stage);
+        if (part == 0 && it / NSTAGES < 128) SCN_TL(65 + my_stage * 256 + 2 * (it / NSTAGES));
+      }
+    }
+  } else if (warp == NPW + 1) {
+    // ------------------------------------------------------------ weight TMA (one thread)
+    if (lane == 0) {
+      int s = 0, ki = 0, kb = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < T; ++it) {
+        mbar_wait_sleep(wempty + s, ph ^ 1u, 200);
+        mbar_arrive_expect_tx(wfull + s, b_bytes);
+        tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, klist[ki] * w_rows_per_k + w_row0, wfull + s);
+        if (++ki == nk) { ki = 0; ++kb; }
+        if (++s == nw) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull);
+    int s = 0, ws = 0, ki = 0, kb = 0;
+    uint32_t ph = 0, wph = 0;
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(wfull + ws, wph);
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      if (it < 256) SCN_TL(1088 + 2 * it);
+      const int nj = min(32, Cin - kb * 32) >> 3;
+      const uint32_t a_lo = desc_lo0 + ((a_base + (uint32_t)s * a_bytes) >> 4);
+      const uint32_t b_lo = desc_lo0 + ((b_base + (uint32_t)ws * b_bytes) >> 4);
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j)
+        mma_tf32(tmem, desc_hi | (uint64_t)(a_lo + 2 * j), desc_hi | (uint64_t)(b_lo + 2 * j), idesc, (it | j) ? 1u : 0u);
+      mma_commit(empty + s);
+      mma_commit(wempty + ws);
+      if (it < 256) SCN_TL(1089 + 2 * it);
+      if (++ki == nk) { ki = 0; ++kb; }
+      if (++s == NSTAGES) { s = 0; ph ^= 1u; }
+      if (++ws == nw) { ws = 0; wph ^= 1u; }
+    }
+    mma_commit(accum);
+  }
+
+  if (warp < NPW) {
+    // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    // warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows); the four warps of a lane quarter split the column chunks
+    if (T > 0) {
+      mbar_wait_sleep(accum, 0, 1000);
+      tc_fence_after();
+    }
+    if (tid == 0) SCN_TL(2);
+    const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    const int q = warp & 3;
+    const int row = sorow[q * 32 + lane];
+    for (int c0 = 16 * (warp >> 2); c0 < Cout; c0 += 16 * (NPW / 4)) {
+      float v[16];
+      if (T > 0) {
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      if (row >= 0) {
+        if (addend) {
+          const float *ad = addend + (int64_t)row * ldadd + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(ad + i);
+        }
+        float *o = out + (int64_t)row * ldo + c0;
+        if (vec) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4 *>(o + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = v[i];
+        }
+      }
+    }
+  }
+  if (tid == 0) SCN_TL(3);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPW) tmem_dealloc<NT>(tmem);
+}
+
+template <uint32_t NT, int NSTAGES>
+static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, const float *A, int64_t lda, const int32_t *nbr,
+                       const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
+                       const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
+                       const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k, int w_row0,
+                       cudaStream_t st) {
+  auto kern = halo_conv_tc_kernel<NT, NSTAGES>;
+  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
+  alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
+  if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
+  kern<<<(unsigned)tiles, 32 * (kHaloWarps + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask,
+                                                                hcap, (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc,
+                                                                L, nw, w_rows_per_k, w_row0);
+  return 0;
+}
+
+static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm, const uint16_t *lmap,
+                          const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
+                          const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
+                          int64_t ldo, int w_rows_per_k, int w_row0, cudaStream_t st) {
+  // two stage images when that lets two CTAs share an SM (one CTA's halo load and epilogue then hide behind the other's
+  // stage building), otherwise four
+  // (the weight ring takes whatever shared memory is left, up to kHaloMaxW slots)
+  const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
+  auto fit = [&](int nst, uint32_t budget, int min_nw, int &nw_out) {
+    int nw = kHaloMaxW;
+    while (nw > min_nw && halo_layout(nst, nw, Cout, hcap).total > budget) --nw;
+    nw_out = nw;
+    return halo_layout(nst, nw, Cout, hcap).total <= budget;
+  };
+  int nstages = 2, nw = 0;
+  int force = 0;
+  if (const char *e = getenv("B200SCN_HALO_STAGES")) force = atoi(e) == 4 ? 4 : 2;   // experiment hook
+  if (force == 4 || !fit(2, half, force == 2 ? 2 : 4, nw)) {
+    nstages = 4;
+    if (!fit(4, whole, 2, nw)) {
+      nstages = 2;
+      if (!fit(2, whole, 2, nw))
+        return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
+    }
+  }
+  const HaloSmem L = halo_layout(nstages, nw, Cout, hcap);
+  const int64_t tiles = ceil_div(n, kTile);
+  int rc;
+#define SCN_ARGS tiles, L, nw, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
+  if (nstages == 2) {
+    if (Cout <= 32) rc = launch_halo<32, 2>(SCN_ARGS);
+    else if (Cout <= 64) rc = launch_halo<64, 2>(SCN_ARGS);
+    else if (Cout <= 128) rc = launch_halo<128, 2>(SCN_ARGS);
+    else rc = launch_halo<256, 2>(SCN_ARGS);
+  } else {
+    if (Cout <= 32) rc = launch_halo<32, 4>(SCN_ARGS);
+    else if (Cout <= 64) rc = launch_halo<64, 4>(SCN_ARGS);
+    else if (Cout <= 128) rc = launch_halo<128, 4>(SCN_ARGS);
+    else rc = launch_halo<256, 4>(SCN_ARGS);
+  }
+#undef SCN_ARGS
+  if (rc) return rc;
+  SCN_CHECK_LAUNCH("subm_conv_tiled");
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace b200scn
+
+using namespace b200scn;
+
+extern "C" {
+
+/* diagnostic (not in the public header): subsequent b200scn_subm_conv_tiled launches record a clock64 timeline of the CTA
+ * that owns `tile` into buf (1600 int64, device); buf = NULL switches it off */
+int b200scn_debug_timeline(long long *buf, int tile) {
+  SCN_CUDA(cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf)));
+  SCN_CUDA(cudaMemcpyToSymbol(g_timeline_tile, &tile, sizeof(tile)));
+  return 0;
+}
+
+int b200scn_morton_keys(const uint64_t *ukeys, int64_t n, uint64_t *mkeys, void *stream) {
+  if (n <= 0) return 0;
+  morton_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ukeys, n, mkeys);
+  SCN_CHECK_LAUNCH("morton_keys");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hcap, uint16_t *lmap,
+                      int32_t *halo_ids, int32_t *halo_n, uint32_t *kmask, void *stream) {
+  if (n <= 0) return 0;
+  if (hcap < 8 || hcap > 1024 || (hcap & 7)) return set_error("tile_plan: hcap=%d must be a multiple of 8 in [8,1024]", hcap);
+  if (n >= ((int64_t)1 << 31)) return set_error("tile_plan: too many rows");
+  if (reinterpret_cast<uintptr_t>(lmap) & 15) return set_error("tile_plan: lmap must be 16-byte aligned");
+  const size_t smem = sizeof(int) * (kTileMap + kPlanHash) + sizeof(unsigned short) * kPlanHash;
+  SCN_CUDA(cudaFuncSetAttribute(tile_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tile_plan_kernel<<<(unsigned)ceil_div(n, kTile), kPlanThreads, smem, (cudaStream_t)stream>>>(
+      nbr, perm, (int)n, hcap, lmap, halo_ids, halo_n, kmask);
+  SCN_CHECK_LAUNCH("tile_plan");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm,
+                            const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
+                            const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream) {
+  if (n <= 0) return 0;
+  if (!b200scn_gather_conv_tf32_ok(Cin, Cout, lda) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(Wkm) & 15))
+    return set_error("subm_conv_tiled: needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 1024, 16-byte aligned rows "
+                     "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
+  if (hcap < 8 || hcap > 1024 || (hcap & 7)) return set_error("subm_conv_tiled: bad hcap %d", hcap);
+  // output channels beyond 256 (the widest tcgen05 N) are produced by separate launches over column slices
+  for (int n0 = 0; n0 < Cout; n0 += 256) {
+    const int nc = Cout - n0 < 256 ? Cout - n0 : 256;
+    if (halo_conv_part(A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, nc,
+                       addend ? addend + n0 : nullptr, ldadd, out + n0, ldo, Cout, n0, (cudaStream_t)stream))
+      return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

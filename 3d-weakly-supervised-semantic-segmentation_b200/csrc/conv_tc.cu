@@ -58,6 +58,11 @@ static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, 
   return 0;
 }
 
+// shared with conv_halo.cu
+int make_weight_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows) {
+  return make_tmap(m, base, rows, cols, ld, box_rows);
+}
+
 constexpr int kTcThreads = 160;
 constexpr int kMaxStages = 4;
 

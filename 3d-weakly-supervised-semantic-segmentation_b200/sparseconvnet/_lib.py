@@ -37,6 +37,9 @@ SIGNATURES = {
     "b200scn_pair_lists": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200scn_gather_conv_tf32_ok": (_i32, [_i32, _i32, _i64]),
     "b200scn_gather_conv": (_i32, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "b200scn_morton_keys": (_i32, [_vp, _i64, _vp, _vp]),
+    "b200scn_tile_plan": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200scn_subm_conv_tiled": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
     "b200scn_scatter_conv": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),

@@ -30,6 +30,13 @@ class Level:
         self.nbr_counts = None    # (27,) int32 device: rules per offset
         self.pairs = None         # (pair_in, pair_out, offsets_dev)
         self._counts = None
+        self.plan = None          # TilePlan of the spatially tiled convolution
+
+    def tile_plan(self, hcap):
+        """Morton-ordered 128-row tiles + per-tile halo lists (b200scn_tile_plan), built once per level and step."""
+        if self.plan is None or self.plan.hcap != hcap:
+            self.plan = TilePlan(self, hcap)
+        return self.plan
 
     def subm_map(self):
         if self.nbr is None:
@@ -59,6 +66,28 @@ class Level:
         if self.pairs is None:
             self.pairs = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()))
         return self.pairs
+
+
+class TilePlan:
+    """perm (n,) int32 site ids along the Morton curve; lmap (T,27,128) uint16; halo_ids (T,hcap) int32; halo_n, kmask (T,)."""
+
+    def __init__(self, level, hcap):
+        nbr = level.subm_map()
+        dev = nbr.device
+        n = level.n
+        st = _lib.stream_for(nbr)
+        mk = alloc_flat(n, dev, torch.int64)
+        check(lib.b200scn_morton_keys(ptr(level.ukeys), n, ptr(mk), st))
+        # sorting the curve keys is plumbing (torch's radix sort); keys are unique, b < 2^15 keeps them positive
+        self.perm = torch.sort(mk)[1].to(torch.int32)
+        T = (n + 127) // 128
+        self.hcap = hcap
+        self.lmap = alloc_flat(T * 27 * 128, dev, torch.int16)
+        self.halo_ids = alloc_flat(T * hcap, dev, torch.int32)
+        self.halo_n = alloc_flat(T, dev, torch.int32)
+        self.kmask = alloc_flat(T, dev, torch.int32)
+        check(lib.b200scn_tile_plan(ptr(nbr), ptr(self.perm), n, hcap, ptr(self.lmap), ptr(self.halo_ids),
+                                    ptr(self.halo_n), ptr(self.kmask), st))
 
 
 def build_pairs(map_t, n, K, total):

@@ -121,6 +121,44 @@ def _use_tf32(gw, lda, x):
     return _precision[0] == 1 and x.data_ptr() % 16 == 0 and lib.b200scn_gather_conv_tf32_ok(gw.cin, gw.cout, lda) == 1
 
 
+# Spatially tiled submanifold convolution (conv_halo.cu): halo capacity per 128-row tile and the smallest level it is
+# used for (below that the gather kernel's offset-split variant wins; B200SCN_HALO=1 forces it on, =0 off).
+_halo = {"hcap": int(os.environ.get("B200SCN_HALO_CAP", "384")), "min_rows": 128 * 148}
+
+
+def set_halo_capacity(hcap):
+    _halo["hcap"] = int(hcap)
+
+
+def _use_tiled(n):
+    mode = os.environ.get("B200SCN_HALO", "")
+    if mode == "0":
+        return False
+    return mode == "1" or n >= _halo["min_rows"]
+
+
+def subm_conv(x, level, gw, addend=None):
+    """out[o] = sum_k x[nbr[o,k]] @ Wg[k] over the level's 3x3x3 neighbour map (forward, and backward-input with the
+    mirrored transposed weights)."""
+    x, ldx = _c(x)
+    if not (_use_tf32(gw, ldx, x) and _use_tiled(level.n)):
+        return gather_conv(x, level.subm_map(), level.n, 27, gw, addend=addend, rules=level)
+    Cin, Cout = gw.cin, gw.cout
+    plan = level.tile_plan(_halo["hcap"])
+    out = alloc_rows(level.n, Cout, x.device)
+    lda = 0
+    if addend is not None:
+        addend, lda = _c(addend)
+    w = gw.kmajor()
+    tok = _p0("gather27", "subm_conv_tiled", 4.0 * (x.shape[0] * Cin + level.n * Cout) + 4.0 * 27 * Cin * Cout,
+              level, 8.0, 2.0 * Cin * Cout)
+    check(lib.b200scn_subm_conv_tiled(ptr(x), ldx, ptr(level.nbr), ptr(plan.perm), ptr(plan.lmap), ptr(plan.halo_ids),
+                                      ptr(plan.halo_n), ptr(plan.kmask), plan.hcap, level.n, ptr(w), Cin, Cout,
+                                      ptr(addend), lda, ptr(out), Cout, _lib.stream_for(x)))
+    _p1(tok)
+    return out
+
+
 def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
     """out[o] = sum_k x[map[o,k]] @ Wg[k] (+ addend[o]);  gw: GemmWeight.  `rules`: rule count (or Level) for accounting."""
     x, ldx = _c(x)
@@ -176,10 +214,9 @@ class SubmanifoldConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, level):
-        nbr = level.subm_map()
         ctx.level = level
         ctx.save_for_backward(x, w)
-        return gather_conv(x, nbr, level.n, 27, GemmWeight(w), rules=level)
+        return subm_conv(x, level, GemmWeight(w))
 
     @staticmethod
     def backward(ctx, g):
@@ -188,7 +225,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
-            dx = gather_conv(g, level.subm_map(), level.n, 27, GemmWeight(w, transposed=True, flip=True), rules=level)
+            dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True))
         if ctx.needs_input_grad[1]:
             pin, pout, offs = level.subm_pairs()
             dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)

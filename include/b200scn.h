@@ -89,6 +89,23 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
                         const float *W, int Cin, int Cout, const float *addend, int64_t ldadd,
                         float *out, int64_t ldo, int precision, void *stream);
 
+/* ---- spatially tiled submanifold convolution (TF32 tcgen05; same result as b200scn_gather_conv(precision = 1) on the
+ * 3x3x3 neighbour map, replaces SubmanifoldConvolution_updateOutput / backward-input).
+ * Plan, once per level:  mkeys[i] = b<<48 | Morton(x,y,z) of ukeys[i]; the caller sorts them and passes the sorting
+ * permutation `perm` (site ids in curve order); tile t = rows perm[128t .. 128t+127].  b200scn_tile_plan fills, per tile,
+ *   halo_ids[t*hcap + s]  the distinct neighbour ids the tile references (first hcap of them), halo_n[t] their number,
+ *   lmap[t*3456 + k*128 + r]  halo slot of nbr[perm[128t+r]*27+k]; 0xFFFF absent, 0xFFFE beyond hcap (fetched through nbr),
+ *   kmask[t]  bit k set iff offset k occurs in the tile.
+ * hcap: multiple of 8 in [8,1024].  lmap must be 16-byte aligned and hold ceil(n/128)*3456 entries. */
+int b200scn_morton_keys(const uint64_t *ukeys, int64_t n, uint64_t *mkeys, void *stream);
+int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hcap, uint16_t *lmap,
+                      int32_t *halo_ids, int32_t *halo_n, uint32_t *kmask, void *stream);
+/* out[o,:] = sum_k A[nbr[o*27+k],:] . W[k] (+ addend[o,:]);  W K-major (27,Cout,Cin); shapes as for precision 1 above. */
+int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm,
+                            const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
+                            const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream);
+
 /* out[map[j*K+k],:] = A[j,:] . W[k] for every present (j,k)   (Deconvolution_updateOutput,
  * Convolution backward-input).  Rows of `out` not addressed by map are left untouched. */
 int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,

@@ -113,3 +113,52 @@ def test_empty_input():
     y = scn.SubmanifoldConvolution(3, 3, 8, 3, False).cuda()(x)
     assert y.features.shape == (0, 8)
     assert scn.OutputLayer(3)(y).shape == (0, 8)
+
+
+def _morton(vox):
+    def spread(v):
+        v = v.astype(np.uint64)
+        out = np.zeros_like(v)
+        for bit in range(16):
+            out |= ((v >> np.uint64(bit)) & np.uint64(1)) << np.uint64(3 * bit)
+        return out
+    return (vox[:, 3].astype(np.uint64) << np.uint64(48)) | (spread(vox[:, 0]) << np.uint64(2)) | \
+        (spread(vox[:, 1]) << np.uint64(1)) | spread(vox[:, 2])
+
+
+@pytest.mark.parametrize("seed,n,extent,batch,hcap", [(0, 500, 12, 2, 384), (5, 6000, 30, 2, 384), (6, 5000, 20, 3, 32)])
+def test_tile_plan(seed, n, extent, batch, hcap):
+    """Spatially tiled convolution plan (conv_halo.cu): Morton order bit-exact against numpy; every lmap entry resolves,
+    through the tile's halo list, to exactly the neighbour id of the rulebook (or is flagged absent / beyond capacity)."""
+    from oracle import scn_oracle as ref
+    coords, feats = random_cloud(seed, n, extent, batch)
+    x = _build(coords, feats)
+    level = x.metadata.levels[4096]
+    _, vox = ref.input_rules(coords.numpy())
+    nbr = ref.subm_map(vox)
+    plan = level.tile_plan(hcap)
+    perm = plan.perm.cpu().numpy()
+    assert np.array_equal(perm, np.argsort(_morton(vox), kind="stable").astype(np.int32))
+    N = vox.shape[0]
+    T = (N + 127) // 128
+    lmap = plan.lmap.cpu().numpy().view(np.uint16).reshape(T, 27, 128)
+    hids = plan.halo_ids.cpu().numpy().reshape(T, hcap)
+    hn = plan.halo_n.cpu().numpy()
+    km = plan.kmask.cpu().numpy().view(np.uint32)
+    saw_overflow = False
+    for t in range(T):
+        rows = perm[t * 128:(t + 1) * 128]
+        sub = nbr[rows]                                   # (r, 27)
+        distinct = np.unique(sub[sub >= 0])
+        assert hn[t] == min(len(distinct), hcap)
+        assert len(np.unique(hids[t, :hn[t]])) == hn[t] and np.isin(hids[t, :hn[t]], distinct).all()
+        lm = lmap[t, :, :len(rows)].T                     # (r, 27)
+        assert (lmap[t, :, len(rows):] == 0xFFFF).all()
+        assert np.array_equal(lm == 0xFFFF, sub < 0)
+        inhalo = lm < 0xFFFE
+        assert np.array_equal(hids[t][lm[inhalo]], sub[inhalo])
+        over = lm == 0xFFFE
+        saw_overflow |= bool(over.any())
+        assert not np.isin(sub[over], hids[t, :hn[t]]).any()
+        assert km[t] == sum(1 << k for k in range(27) if (sub[:, k] >= 0).any())
+    assert saw_overflow == (hcap == 32)
