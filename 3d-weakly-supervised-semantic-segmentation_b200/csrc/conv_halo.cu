@@ -106,8 +106,15 @@ tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ pe
 }
 
 // ------------------------------------------------------------------------------------------------ convolution
-constexpr int kHaloWarps = 16;   // stage-building warps
-constexpr int kHaloMaxStages = 4;
+// Measured on B200 (tools/halo_timeline.py): with BOTH operands in shared memory a tcgen05.mma kind::tf32 of M = 128,
+// K = 8 costs ~120 cycles whatever N is (the A rows are fetched from shared memory at about one 128-byte swizzle row per
+// cycle), i.e. ~270 MAC/cycle/SM = 13 % of the TF32 peak at N = 32..64 -- that, not the gathers, bounded every earlier
+// variant.  Here the A operand lives in TENSOR MEMORY: a builder warp reads its 32 rows of the tile from the halo
+// (shared memory -> registers) and writes them with tcgen05.st straight into the TMEM lanes the MMA reads (lane = tile
+// row, one column per tf32 element); only the small W slice is a shared-memory operand.
+constexpr int kHaloWarps = 16;   // builder warps: warp = 4 * stage + lane quarter
+constexpr int kHaloStages = 4;   // A stage images in TMEM, 32 columns (= 32 channels) each
+constexpr int kHaloMaxW = 16;    // weight-ring slots
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -117,17 +124,38 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+// 32 lanes x 16 consecutive 32-bit columns, registers -> TMEM (lane t of the warp writes TMEM lane base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const float4 &b, const float4 &c, const float4 &d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "f"(c.x), "f"(c.y),
+      "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
+// One lane of a converged warp, chosen by elect.sync.  Measured on B200 (tools/micro/mma_issue_bench.cu, kind::tf32, M = 128,
+// K = 8, A in TMEM): issued from an `if (lane == 0)` region, or with one elect.sync per instruction, a tcgen05.mma costs
+// ~100 cycles of scalar->uniform register moves and votes on the issuing thread whatever N is; issued in a loop that one
+// elected lane runs on its own it costs N/2 cycles (16.5 / 32.3 / 64.0 / 127.4 for N = 32 / 64 / 128 / 256) -- the
+// tensor pipe's real rate.  With A in shared memory the same loop needs 55 / 69 / 97 / 160 cycles.  (elect_one: tc_common.cuh)
 struct HaloSmem {
-  uint32_t a_off, b_off, halo_off, lmap_off, orow_off, hids_off, klist_off, bar_off, total;
+  uint32_t b_off, halo_off, lmap_off, orow_off, hids_off, klist_off, bar_off, total;
 };
 
-constexpr int kHaloMaxW = 16;    // weight-ring slots
-
-static HaloSmem halo_layout(int nstages, int nw, int Cout, int hcap) {
+static HaloSmem halo_layout(int nw, int Cout, int hcap) {
   HaloSmem L;
-  L.a_off = 0;
-  L.b_off = (uint32_t)nstages * kTile * 128;
+  L.b_off = 0;
   L.halo_off = L.b_off + (uint32_t)nw * Cout * 128;
   L.lmap_off = L.halo_off + (uint32_t)hcap * 128;
   L.orow_off = L.lmap_off + ((kTileMap * 2 + 15) & ~15);
@@ -139,43 +167,42 @@ static HaloSmem halo_layout(int nstages, int nw, int Cout, int hcap) {
 }
 
 // Diagnostic: clock64 timeline of ONE CTA (b200scn_debug_timeline).  Slots: [0] start, [1] prologue done, [2] accumulator
-// seen by the epilogue, [3] epilogue done; builders of stage group g (lane 0 of its first warp): 64 + g*256 + 2*use + {0:
-// slot free, 1: built}, halo load of channel block kb: 32 + 2*kb + {0,1}; MMA thread: 1088 + 2*it + {0: operands seen, 1: issued}.
+// seen by the epilogue, [3] epilogue done; builder warp of stage g, quarter 0: 64 + g*256 + 2*use + {0: slot free (= the
+// MMAs of the slot's previous use have completed), 1: built}; halo load of channel block kb: 32 + 2*kb + {0,1}.
 __device__ long long *g_timeline = nullptr;
 __device__ int g_timeline_tile = -1;
 #define SCN_TL(slot) do { if (tl) tl[slot] = clock64(); } while (0)
 
-// NT: TMEM columns (power of two >= Cout); NSTAGES: 2 or 4 stage images, each built by 16 / NSTAGES warps.
-template <uint32_t NT, int NSTAGES>
-__global__ void __launch_bounds__(32 * (kHaloWarps + 2), NSTAGES == 2 ? 2 : 1)
+// NT: TMEM columns allocated (power of two >= acc_cols + 128): accumulator in columns [0, Cout), A stage s in columns
+// [acc_cols + 32 s, + 32).  MINB: CTAs per SM the register budget is sized for.
+template <uint32_t NT, int MINB>
+__global__ void __launch_bounds__(32 * (kHaloWarps + 2), MINB)
 halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
                     const int32_t *__restrict__ nbr, const int32_t *__restrict__ perm,
                     const uint16_t *__restrict__ lmap, const int32_t *__restrict__ halo_ids,
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
-                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int w_rows_per_k, int w_row0) {
+                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int w_rows_per_k, int w_row0) {
   constexpr int NPW = kHaloWarps;
   constexpr int NTHREADS = 32 * (NPW + 2);
-  constexpr int WPS = NPW / NSTAGES;   // warps per stage image
-  constexpr int RPW = kTile / WPS;     // rows per warp
-  constexpr int NI = RPW / 4;          // row slots per lane (8 lanes share a row)
+  constexpr int NS = kHaloStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
-  const uint32_t a_bytes = kTile * 128, b_bytes = (uint32_t)Cout * 128;
-  const uint32_t a_base = base + L.a_off, b_base = base + L.b_off, halo_base = base + L.halo_off;
+  const uint32_t b_bytes = (uint32_t)Cout * 128;
+  const uint32_t b_base = base + L.b_off, halo_base = base + L.halo_off;
   const uint16_t *slmap = reinterpret_cast<const uint16_t *>(sm + L.lmap_off);
   int *sorow = reinterpret_cast<int *>(sm + L.orow_off);
   int *shids = reinterpret_cast<int *>(sm + L.hids_off);
   int *klist = reinterpret_cast<int *>(sm + L.klist_off);
   int *nk_p = klist + 27;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sm + L.bar_off);
-  uint64_t *empty = full + kHaloMaxStages;
-  uint64_t *accum = empty + kHaloMaxStages;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + L.bar_off);   // A stage written (one arrival per builder warp)
+  uint64_t *empty = full + NS;                                      // A stage consumed (tcgen05.commit)
+  uint64_t *accum = empty + NS;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
-  uint64_t *wfull = accum + 2;            // weight ring: its own, deeper pipeline (a W slice is a ~1 us TMA round trip
-  uint64_t *wempty = wfull + kHaloMaxW;   // that depends on nothing in the tile, so it is prefetched `nw` stages ahead)
+  uint64_t *wfull = accum + 2;            // weight ring: its own, deeper pipeline (a W slice is a TMA round trip that
+  uint64_t *wempty = wfull + kHaloMaxW;   // depends on nothing in the tile, so it is prefetched `nw` stages ahead)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, row0 = tile * kTile;
@@ -195,14 +222,13 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       for (int k = 0; k < 27; ++k)
         if ((km >> k) & 1u) klist[n++] = k;
       *nk_p = n;
-      for (int s = 0; s < NSTAGES; ++s) {
-        mbar_init(full + s, 32 * WPS);   // every building lane
+      for (int s = 0; s < NS; ++s) {
+        mbar_init(full + s, 4);    // the four builder warps of the stage (one per lane quarter)
         mbar_init(empty + s, 1);
       }
-      for (int s = 0; s < nw; ++s) {
-        mbar_init(wfull + s, 1);             // the weight TMA's expect_tx arrival
-        mbar_init(wempty + s, 1);
-      }
+      for (int s = 0; s < nw; ++s) mbar_init(wfull + s, 1);   // the weight TMA's expect_tx arrival
+      mbar_init(wempty + 0, 1);    // the ring is released in two halves (one tcgen05.commit per half, not per slot)
+      mbar_init(wempty + 1, 1);
       mbar_init(accum, 1);
       fence_barrier_init();
       tma_prefetch_desc(&tmW);
@@ -218,109 +244,153 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   const int nkb = (Cin + 31) >> 5;
   if (tid == 0) SCN_TL(1);
   const int T = nk * nkb;   // stage (kb, ki) has index it = kb * nk + ki: channel blocks outermost
+  const int a_col0 = acc_cols;
 
   if (warp < NPW) {
-    // ------------------------------------------------------------ halo loaders + stage builders
-    const int c = lane & 7, rl = lane >> 3;
-    const int my_stage = warp % NSTAGES, part = warp / NSTAGES;
-    const int rbase = part * RPW;
-    uint32_t soff[NI];   // swizzled byte offset of this lane's chunk in each of its rows
-    int rws[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      rws[i] = rbase + rl + 4 * i;
-      soff[i] = sw128(rws[i], c);
-    }
-    // `dirty`: which of this lane's row slots of its stage image hold data (the warp owns the same rows of the same
-    // image for the whole tile), so absent neighbours cost a zero store only where stale data must be cleared
-    uint32_t dirty = 0xFFFFFFFFu;
-    const uint32_t a_st = a_base + (uint32_t)my_stage * a_bytes;
-    int it = my_stage;
+    // ------------------------------------------------------------ halo loaders + A-stage builders
+    const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, stage image
+    const int r = q * 32 + lane;                    // this thread's tile row = TMEM lane
+    const uint32_t a_tm = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a_col0 + 32 * g);
+    const int c = tid & 7;                          // chunk this thread copies during halo loads
+    bool dirty = true;                              // the stage image holds data in some row of this warp
+    int it = g;
+    int ws = g;                                     // weight-ring slot of stage `it` (nw >= 4 = NS)
+    uint32_t wph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      const int chan = kb * 32 + c * 4;
+      const int cvalid = min(32, Cin - kb * 32);    // live channels of this block (multiple of 8)
       named_bar_sync(1, 32 * NPW);   // every builder has finished reading the previous channel block's halo
       if (tid == 0) SCN_TL(32 + 2 * kb);
-      if (chan < Cin) {
-        const float *acol = A + chan;
+      if (c * 4 < cvalid) {
+        const float *acol = A + kb * 32 + c * 4;
+        // chunk c of halo row h is stored at position (c + h) & 7, so that lanes reading the same chunk of different
+        // rows spread over the banks
         for (int h = tid >> 3; h < hn; h += 4 * NPW)
-          cp_async16(halo_base + (uint32_t)h * 128 + c * 16, acol + (int64_t)shids[h] * lda, 16u);
+          cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)shids[h] * lda, 16u);
       }
       cp_async_wait_all();
       named_bar_sync(1, 32 * NPW);   // halo complete and visible to all builders
       if (tid == 0) SCN_TL(33 + 2 * kb);
       const int it_end = (kb + 1) * nk;
-      for (; it < it_end; it += NSTAGES) {
-        const uint32_t ph = (uint32_t)(it / NSTAGES) & 1u;
-        mbar_wait_sleep(empty + my_stage, ph ^ 1u, 200);
-        if (part == 0 && it / NSTAGES < 128) SCN_TL(64 + my_stage * 256 + 2 * (it / NSTAGES));
-        const int k = klist[it - kb * nk];
-        if (chan < Cin) {
-          uint32_t slot[NI];
-#pragma unroll
-          for (int i = 0; i < NI; ++i) slot[i] = slmap[k * kTile + rws[i]];   // all map reads first
-          float4 v[NI];
-#pragma unroll
-          for (int i = 0; i < NI; ++i) {
-            if (slot[i] < kOverflow) {
-              v[i] = lds_f4(halo_base + slot[i] * 128 + c * 16);
-            } else if (slot[i] == kOverflow) {   // beyond the halo capacity: through the global neighbour map
-              const int idx = __ldg(nbr + (int64_t)sorow[rws[i]] * 27 + k);
-              v[i] = ldg_f4(A + (int64_t)idx * lda + chan);
-            } else {
-              v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < NI; ++i) {
-            const bool present = slot[i] != kAbsent;
-            if (present || ((dirty >> i) & 1u)) sts_f4(a_st + soff[i], v[i]);
-            dirty = present ? (dirty | (1u << i)) : (dirty & ~(1u << i));
+      // Software pipeline: the first half of this warp's row of its NEXT stage is read from the halo into registers while
+      // the tensor pipe still owns the stage image (the whole row would not fit the 56-register budget of two CTAs per
+      // SM); the second half is fetched right after "slot free", under the first half's TMEM store.
+      float4 v0, v1, v2, v3;
+      uint32_t slot = kAbsent;
+      int k = 0;
+      bool any = false;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto load_half = [&](int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
+        a0 = a1 = a2 = a3 = z;
+        if (slot < kOverflow) {
+          const uint32_t rb = halo_base + slot * 128;
+          a0 = lds_f4(rb + (((slot + 4 * hf + 0) & 7u) << 4));
+          a1 = lds_f4(rb + (((slot + 4 * hf + 1) & 7u) << 4));
+          a2 = lds_f4(rb + (((slot + 4 * hf + 2) & 7u) << 4));
+          a3 = lds_f4(rb + (((slot + 4 * hf + 3) & 7u) << 4));
+        } else if (slot == kOverflow) {   // beyond the halo capacity: through the global neighbour map
+          const int idx = __ldg(nbr + (int64_t)sorow[r] * 27 + k);
+          const float *src = A + (int64_t)idx * lda + kb * 32 + hf * 16;
+          a0 = ldg_f4(src);
+          a1 = ldg_f4(src + 4);
+          if (hf * 16 + 8 < cvalid) {
+            a2 = ldg_f4(src + 8);
+            a3 = ldg_f4(src + 12);
           }
         }
-        fence_proxy_async();
-        mbar_arrive(full + my_stage);
-        if (part == 0 && it / NSTAGES < 128) SCN_TL(65 + my_stage * 256 + 2 * (it / NSTAGES));
+      };
+      auto prefetch = [&](int it_) {
+        k = klist[it_ - kb * nk];
+        slot = slmap[k * kTile + r];
+        any = __any_sync(0xffffffffu, slot != kAbsent);
+        load_half(0, v0, v1, v2, v3);
+      };
+      if (it < it_end) prefetch(it);
+      for (; it < it_end; it += NS) {
+        const uint32_t ph = (uint32_t)(it / NS) & 1u;
+        // quarter 0 also vouches for the stage's weight slice, so the MMA thread polls ONE barrier per stage
+        if (q == 0 && lane == 0) mbar_wait(wfull + ws, wph);
+        mbar_wait_sleep(empty + g, ph ^ 1u, 100);
+        tc_fence_after();
+        if (q == 0 && it / NS < 128) SCN_TL(64 + g * 256 + 2 * (it / NS));
+        if (any || dirty) {
+          if (cvalid > 16) {
+            float4 u0, u1, u2, u3;
+            load_half(1, u0, u1, u2, u3);
+            tmem_st16(a_tm, v0, v1, v2, v3);
+            tmem_st16(a_tm + 16, u0, u1, u2, u3);
+          } else {
+            tmem_st16(a_tm, v0, v1, v2, v3);
+          }
+          tmem_st_wait();
+        }
+        dirty = any;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + g);
+        ws += NS;
+        if (ws >= nw) { ws -= nw; wph ^= 1u; }
+        if (q == 0 && it / NS < 128) SCN_TL(65 + g * 256 + 2 * (it / NS));
+        if (it + NS < it_end) prefetch(it + NS);
       }
     }
   } else if (warp == NPW + 1) {
     // ------------------------------------------------------------ weight TMA (one thread)
     if (lane == 0) {
+      const int wh = nw >> 1;
       int s = 0, ki = 0, kb = 0;
       uint32_t ph = 0;
       for (int it = 0; it < T; ++it) {
-        mbar_wait_sleep(wempty + s, ph ^ 1u, 200);
+        if (s == 0) mbar_wait_sleep(wempty + 0, ph ^ 1u, 200);
+        else if (s == wh) mbar_wait_sleep(wempty + 1, ph ^ 1u, 200);
         mbar_arrive_expect_tx(wfull + s, b_bytes);
         tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, klist[ki] * w_rows_per_k + w_row0, wfull + s);
         if (++ki == nk) { ki = 0; ++kb; }
         if (++s == nw) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
+  } else if (elect_one()) {
+    // ------------------------------------------------------------ MMA issuer (one elected lane runs the whole loop)
+    // This thread's dependent instruction chain paces the whole CTA (every instruction of it competes with ~9 warps for
+    // its scheduler), so the loop is kept minimal: stage index and phase are compile-time (unrolled by NS), descriptors
+    // advance by additions, one barrier wait per stage (the stage's quarter-0 builder vouches for the W slice).
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
-    const uint32_t desc_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull);
-    int s = 0, ws = 0, ki = 0, kb = 0;
-    uint32_t ph = 0, wph = 0;
-    for (int it = 0; it < T; ++it) {
-      mbar_wait(wfull + ws, wph);
-      mbar_wait(full + s, ph);
-      tc_fence_after();
-      if (it < 256) SCN_TL(1088 + 2 * it);
-      const int nj = min(32, Cin - kb * 32) >> 3;
-      const uint32_t a_lo = desc_lo0 + ((a_base + (uint32_t)s * a_bytes) >> 4);
-      const uint32_t b_lo = desc_lo0 + ((b_base + (uint32_t)ws * b_bytes) >> 4);
-#pragma unroll 4
-      for (int j = 0; j < nj; ++j)
-        mma_tf32(tmem, desc_hi | (uint64_t)(a_lo + 2 * j), desc_hi | (uint64_t)(b_lo + 2 * j), idesc, (it | j) ? 1u : 0u);
-      mma_commit(empty + s);
-      mma_commit(wempty + ws);
-      if (it < 256) SCN_TL(1089 + 2 * it);
-      if (++ki == nk) { ki = 0; ++kb; }
-      if (++s == NSTAGES) { s = 0; ph ^= 1u; }
-      if (++ws == nw) { ws = 0; wph ^= 1u; }
+    const uint32_t b_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull) + (b_base >> 4);
+    const uint32_t b_step = b_bytes >> 4;
+    const uint32_t a_tm0 = tmem + (uint32_t)a_col0;
+    const int wh = nw >> 1;
+    const int nj_last = ((Cin - 1) & 31) + 1 >> 3;   // K = 8 steps of the last channel block (4 when Cin % 32 == 0)
+    const int it_last = (nkb - 1) * nk;              // first stage of the last channel block
+    int ws = 0;
+    uint32_t b_lo = b_lo0, ph = 0, accf = 0;
+    for (int it0 = 0; it0 < T; it0 += NS) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int it = it0 + s;
+        if (it < T) {
+          mbar_wait(full + s, ph);   // A stage written AND its W slice landed
+          tc_fence_after();
+          const uint32_t a_tm = a_tm0 + 32 * s;
+          if (nj_last == 4 || it < it_last) {
+            mma_tf32_ts(tmem, a_tm, desc_hi | (uint64_t)b_lo, idesc, accf);
+            mma_tf32_ts(tmem, a_tm + 8, desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
+            mma_tf32_ts(tmem, a_tm + 16, desc_hi | (uint64_t)(b_lo + 4), idesc, 1u);
+            mma_tf32_ts(tmem, a_tm + 24, desc_hi | (uint64_t)(b_lo + 6), idesc, 1u);
+          } else {
+            for (int j = 0; j < nj_last; ++j)
+              mma_tf32_ts(tmem, a_tm + 8 * j, desc_hi | (uint64_t)(b_lo + 2 * j), idesc, j ? 1u : accf);
+          }
+          accf = 1u;
+          mma_commit(empty + s);
+          b_lo += b_step;
+          if (++ws == wh) mma_commit(wempty + 0);
+          else if (ws == nw) { mma_commit(wempty + 1); ws = 0; b_lo = b_lo0; }
+        }
+      }
+      ph ^= 1u;
     }
     mma_commit(accum);
   }
+  __syncwarp();
 
   if (warp < NPW) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
@@ -365,20 +435,20 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   if (warp == NPW) tmem_dealloc<NT>(tmem);
 }
 
-template <uint32_t NT, int NSTAGES>
-static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, const float *A, int64_t lda, const int32_t *nbr,
-                       const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
-                       const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
-                       const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k, int w_row0,
-                       cudaStream_t st) {
-  auto kern = halo_conv_tc_kernel<NT, NSTAGES>;
+template <uint32_t NT, int MINB>
+static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, const float *A, int64_t lda,
+                       const int32_t *nbr, const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids,
+                       const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin,
+                       int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k,
+                       int w_row0, cudaStream_t st) {
+  auto kern = halo_conv_tc_kernel<NT, MINB>;
   SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
   if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
   kern<<<(unsigned)tiles, 32 * (kHaloWarps + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask,
                                                                 hcap, (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc,
-                                                                L, nw, w_rows_per_k, w_row0);
+                                                                L, nw, acc_cols, w_rows_per_k, w_row0);
   return 0;
 }
 
@@ -386,42 +456,31 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
                           const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
                           const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
                           int64_t ldo, int w_rows_per_k, int w_row0, cudaStream_t st) {
-  // two stage images when that lets two CTAs share an SM (one CTA's halo load and epilogue then hide behind the other's
-  // stage building), otherwise four
-  // (the weight ring takes whatever shared memory is left, up to kHaloMaxW slots)
+  // TMEM: accumulator (Cout columns, rounded to 32) + four A stages of 32 columns.  Up to 256 columns two CTAs share an
+  // SM (one CTA's halo load, prologue and epilogue hide behind the other's stages) if shared memory allows it too; the
+  // weight ring takes whatever shared memory is left, up to kHaloMaxW slots.
+  const int acc_cols = (Cout + 31) & ~31;
+  const int a_cols = 32 * kHaloStages;
+  const int cols = acc_cols + a_cols;
   const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
-  auto fit = [&](int nst, uint32_t budget, int min_nw, int &nw_out) {
+  auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 4 (one slot per A stage), <= kHaloMaxW
     int nw = kHaloMaxW;
-    while (nw > min_nw && halo_layout(nst, nw, Cout, hcap).total > budget) --nw;
+    while (nw > 4 && halo_layout(nw, Cout, hcap).total > budget) nw -= 2;
     nw_out = nw;
-    return halo_layout(nst, nw, Cout, hcap).total <= budget;
+    return halo_layout(nw, Cout, hcap).total <= budget;
   };
-  int nstages = 2, nw = 0;
-  int force = 0;
-  if (const char *e = getenv("B200SCN_HALO_STAGES")) force = atoi(e) == 4 ? 4 : 2;   // experiment hook
-  if (force == 4 || !fit(2, half, force == 2 ? 2 : 4, nw)) {
-    nstages = 4;
-    if (!fit(4, whole, 2, nw)) {
-      nstages = 2;
-      if (!fit(2, whole, 2, nw))
-        return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
-    }
-  }
-  const HaloSmem L = halo_layout(nstages, nw, Cout, hcap);
+  int nw = 0;
+  bool two = cols <= 256 && fit(half, nw);
+  if (const char *e = getenv("B200SCN_HALO_CTAS")) two = two && atoi(e) != 1;   // experiment hook
+  if (!two && !fit(whole, nw))
+    return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
+  const HaloSmem L = halo_layout(nw, Cout, hcap);
   const int64_t tiles = ceil_div(n, kTile);
   int rc;
-#define SCN_ARGS tiles, L, nw, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
-  if (nstages == 2) {
-    if (Cout <= 32) rc = launch_halo<32, 2>(SCN_ARGS);
-    else if (Cout <= 64) rc = launch_halo<64, 2>(SCN_ARGS);
-    else if (Cout <= 128) rc = launch_halo<128, 2>(SCN_ARGS);
-    else rc = launch_halo<256, 2>(SCN_ARGS);
-  } else {
-    if (Cout <= 32) rc = launch_halo<32, 4>(SCN_ARGS);
-    else if (Cout <= 64) rc = launch_halo<64, 4>(SCN_ARGS);
-    else if (Cout <= 128) rc = launch_halo<128, 4>(SCN_ARGS);
-    else rc = launch_halo<256, 4>(SCN_ARGS);
-  }
+#define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
+  if (two) rc = launch_halo<256, 2>(SCN_ARGS);
+  else if (cols <= 256) rc = launch_halo<256, 1>(SCN_ARGS);
+  else rc = launch_halo<512, 1>(SCN_ARGS);
 #undef SCN_ARGS
   if (rc) return rc;
   SCN_CHECK_LAUNCH("subm_conv_tiled");

@@ -231,8 +231,8 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
         if (++s == nstages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (lane == 0) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
+  } else if (elect_one()) {
+    // ------------------------------------------------------------ MMA issuer (one elected thread, see elect_one)
     // Descriptors differ only in the 14-bit start-address field: build the constant part once and patch the low word
     // with 32-bit adds (this single thread's dependent instruction chain is on the consumer's critical path).
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
@@ -514,7 +514,7 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
       fence_proxy_async();
       mbar_arrive(full + s);
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // constant descriptor part once, 32-bit patching of the start address per MMA (see the gather kernel)
     const uint64_t desc_hi = make_smem_desc(0, blk, 512, 1) & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = (uint32_t)(make_smem_desc(0, blk, 512, 1) & 0xFFFFFFFFull);

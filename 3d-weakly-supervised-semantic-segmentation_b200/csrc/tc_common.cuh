@@ -57,6 +57,14 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 
 // ---------------------------------------------------------------- tcgen05
+// One lane of a CONVERGED warp (elect.sync).  The thread that issues tcgen05.mma must be chosen this way: inside an
+// `if (lane == 0)` region the compiler cannot prove a single active thread and wraps every tcgen05 instruction in an
+// elect / vote / branch loop (~100 cycles per MMA on the issuing thread, tools/micro/mma_issue_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok));
+  return ok != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

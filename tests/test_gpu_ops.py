@@ -9,7 +9,7 @@ TOL = 1e-4
 TOL_TF32 = 2e-3   # TF32 operands (10-bit mantissa), fp32 accumulate: the stated tensor-core tolerance
 
 
-@pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3", "tf32-tma", "tf32-halo", "tf32-halo4", "tf32-halo-ovf"])
+@pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3", "tf32-tma", "tf32-halo", "tf32-halo1", "tf32-halo-ovf"])
 def precision(request):
     """fp32 CUDA-core path, TF32 tcgen05 path, and the TF32 path with its large-level (256-row CTAs) and tiny-level
     (offsets split over CTAs) variants forced on, which the heuristics would not pick at test sizes."""
@@ -23,11 +23,11 @@ def precision(request):
         os.environ["B200SCN_TC_NSPLIT"] = "3"
     if name == "tf32-tma":
         os.environ["B200SCN_TC_TMA"] = "1"
-    # spatially tiled submanifold kernel (conv_halo.cu) forced on at test sizes: two / four stage images, and a halo
+    # spatially tiled submanifold kernel (conv_halo.cu) forced on at test sizes: two CTAs or one per SM, and a halo
     # capacity so small that most neighbours take the beyond-capacity route through the global map
     os.environ["B200SCN_HALO"] = "1" if name.startswith("tf32-halo") else "0"
-    if name == "tf32-halo4":
-        os.environ["B200SCN_HALO_STAGES"] = "4"
+    if name == "tf32-halo1":
+        os.environ["B200SCN_HALO_CTAS"] = "1"
     if name == "tf32-halo-ovf":
         scn.ops.set_halo_capacity(64)
     yield "fp32" if name == "fp32" else "tf32"
@@ -35,7 +35,7 @@ def precision(request):
     os.environ.pop("B200SCN_TC_NSPLIT", None)
     os.environ.pop("B200SCN_TC_TMA", None)
     os.environ.pop("B200SCN_HALO", None)
-    os.environ.pop("B200SCN_HALO_STAGES", None)
+    os.environ.pop("B200SCN_HALO_CTAS", None)
     scn.ops.set_halo_capacity(384)
     scn.set_precision("fp32")
 

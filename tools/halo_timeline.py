@@ -16,7 +16,7 @@ conv = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
 f = torch.randn(level.n, cin, device='cuda')
 gw = ops.GemmWeight(conv.weight.view(27, cin, cout))
 for _ in range(3): ops.subm_conv(f, level, gw)
-buf = torch.zeros(1600, dtype=torch.int64, device='cuda')
+buf = torch.zeros(4096, dtype=torch.int64, device='cuda')
 tile = (level.n // 128) // 2
 fn = _lib.lib.b200scn_debug_timeline; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert fn(buf.data_ptr(), tile) == 0
@@ -32,3 +32,4 @@ for g in range(4):
     if rows: print("builder group", g, " (slot free, built):", rows[:30])
 mm = [(r(1088 + 2 * i), r(1089 + 2 * i)) for i in range(256) if t[1088 + 2 * i]]
 print("mma (operands seen, issued):", mm[:60])
+print("mma (after mmas, after commit1):", [(r(1600 + 2 * i), r(1601 + 2 * i)) for i in range(128) if t[1600 + 2 * i]][:60])
