@@ -112,8 +112,7 @@ tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ pe
 // variant.  Here the A operand lives in TENSOR MEMORY: a builder warp reads its 32 rows of the tile from the halo
 // (shared memory -> registers) and writes them with tcgen05.st straight into the TMEM lanes the MMA reads (lane = tile
 // row, one column per tf32 element); only the small W slice is a shared-memory operand.
-constexpr int kHaloWarps = 16;   // builder warps: warp = 4 * stage + lane quarter
-constexpr int kHaloStages = 4;   // A stage images in TMEM, 32 columns (= 32 channels) each
+constexpr int kHaloMaxSlots = 4;   // A slots in TMEM (64 columns = two stages of 32 channels each)
 constexpr int kHaloMaxW = 16;    // weight-ring slots
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -173,19 +172,21 @@ __device__ long long *g_timeline = nullptr;
 __device__ int g_timeline_tile = -1;
 #define SCN_TL(slot) do { if (tl) tl[slot] = clock64(); } while (0)
 
-// NT: TMEM columns allocated (power of two >= acc_cols + 128): accumulator in columns [0, Cout), A stage s in columns
-// [acc_cols + 32 s, + 32).  MINB: CTAs per SM the register budget is sized for.
-template <uint32_t NT, int MINB>
-__global__ void __launch_bounds__(32 * (kHaloWarps + 2), MINB)
+// NT: TMEM columns allocated (power of two >= acc_cols + 64 NS): accumulator in columns [0, Cout), A slot s in columns
+// [acc_cols + 64 s, + 64).  A slot holds TWO stages (two kernel offsets x 32 channels, 8 tcgen05.mma): every barrier
+// round trip -- builder <-> MMA thread <-> tensor pipe -- costs a few hundred cycles of dependent instructions on the
+// single issuing thread whatever the amount of work, so it is paid once per 8 MMAs.  4 NS builder warps
+// (warp = 4 * slot + TMEM lane quarter).  MINB: CTAs per SM the register budget is sized for.
+template <uint32_t NT, int NS, int MINB>
+__global__ void __launch_bounds__(32 * (4 * NS + 2), MINB)
 halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
                     const int32_t *__restrict__ nbr, const int32_t *__restrict__ perm,
                     const uint16_t *__restrict__ lmap, const int32_t *__restrict__ halo_ids,
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
                     int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int w_rows_per_k, int w_row0) {
-  constexpr int NPW = kHaloWarps;
+  constexpr int NPW = 4 * NS;
   constexpr int NTHREADS = 32 * (NPW + 2);
-  constexpr int NS = kHaloStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -197,9 +198,9 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   int *shids = reinterpret_cast<int *>(sm + L.hids_off);
   int *klist = reinterpret_cast<int *>(sm + L.klist_off);
   int *nk_p = klist + 27;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sm + L.bar_off);   // A stage written (one arrival per builder warp)
-  uint64_t *empty = full + NS;                                      // A stage consumed (tcgen05.commit)
-  uint64_t *accum = empty + NS;
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + L.bar_off);   // A slot written (one arrival per builder warp)
+  uint64_t *empty = full + kHaloMaxSlots;                           // A slot consumed (tcgen05.commit)
+  uint64_t *accum = empty + kHaloMaxSlots;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
   uint64_t *wfull = accum + 2;            // weight ring: its own, deeper pipeline (a W slice is a TMA round trip that
   uint64_t *wempty = wfull + kHaloMaxW;   // depends on nothing in the tile, so it is prefetched `nw` stages ahead)
@@ -210,12 +211,34 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   long long *tl = (g_timeline && g_timeline_tile == tile && lane == 0) ? g_timeline : nullptr;
   if (tid == 0) SCN_TL(0);
 
-  // ---- prologue: the tile's plan slice -> shared memory
+  // ---- prologue: the tile's plan slice -> shared memory.  Every builder thread fetches the halo row ids it copies (rows
+  // tid/8 + 4*NPW*j) in the same global round trip as halo_n and issues the first channel block's halo copies straight
+  // from registers, before the CTA-wide set-up (TMEM allocation, barriers) completes; later blocks read the ids from smem.
+  constexpr int kHidSlots = (512 + 4 * NPW - 1) / (4 * NPW);   // hcap <= 512
   {
     const uint16_t *src = lmap + (int64_t)tile * kTileMap;   // 6912 bytes, 16-byte aligned
     for (int e = tid; e < kTileMap * 2 / 16; e += NTHREADS) cp_async16(base + L.lmap_off + e * 16, src + e * 8, 16u);
+    if (warp < NPW) {
+      const int32_t *ids = halo_ids + (int64_t)tile * hcap;
+      const int c = tid & 7;
+      int hid[kHidSlots];
+#pragma unroll
+      for (int j = 0; j < kHidSlots; ++j) {
+        const int h = (tid >> 3) + 4 * NPW * j;
+        hid[j] = h < hcap ? __ldg(ids + h) : 0;   // entries at and beyond halo_n are never dereferenced
+      }
+      const float *acol = A + c * 4;
+#pragma unroll
+      for (int j = 0; j < kHidSlots; ++j) {
+        const int h = (tid >> 3) + 4 * NPW * j;
+        if (h < hn) {
+          if (c == 0) shids[h] = hid[j];
+          if (c * 4 < Cin)
+            cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)hid[j] * lda, 16u);
+        }
+      }
+    }
     if (tid < kTile) sorow[tid] = row0 + tid < n_rows ? __ldg(perm + row0 + tid) : -1;
-    for (int i = tid; i < hn; i += NTHREADS) shids[i] = __ldg(halo_ids + (int64_t)tile * hcap + i);
     if (tid == 0) {
       const uint32_t km = __ldg(kmask + tile);
       int n = 0;
@@ -223,7 +246,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         if ((km >> k) & 1u) klist[n++] = k;
       *nk_p = n;
       for (int s = 0; s < NS; ++s) {
-        mbar_init(full + s, 4);    // the four builder warps of the stage (one per lane quarter)
+        mbar_init(full + s, 4);    // the four builder warps of the slot (one per lane quarter)
         mbar_init(empty + s, 1);
       }
       for (int s = 0; s < nw; ++s) mbar_init(wfull + s, 1);   // the weight TMA's expect_tx arrival
@@ -233,8 +256,18 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       fence_barrier_init();
       tma_prefetch_desc(&tmW);
     }
-    cp_async_wait_all();
   }
+  // halo of channel block kb: chunk c of halo row h is stored at position (c + h) & 7, so that lanes reading the same
+  // chunk of different rows spread over the banks
+  auto load_halo = [&](int kb) {
+    const int c = tid & 7;
+    if (c * 4 < min(32, Cin - kb * 32)) {
+      const float *acol = A + kb * 32 + c * 4;
+      for (int h = tid >> 3; h < hn; h += 4 * NPW)
+        cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)shids[h] * lda, 16u);
+    }
+  };
+  cp_async_wait_all();
   if (warp == NPW) tmem_alloc<NT>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -243,43 +276,39 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   const int nk = *nk_p;
   const int nkb = (Cin + 31) >> 5;
   if (tid == 0) SCN_TL(1);
-  const int T = nk * nkb;   // stage (kb, ki) has index it = kb * nk + ki: channel blocks outermost
+  // Stage (kb, ki) -- channel block kb outermost, ki-th present offset -- has index kb * nk + ki and uses weight-ring
+  // slot (kb * nk + ki) % nw.  Slot visit (kb, p) covers stages ki = 2p and 2p + 1 (the latter missing when nk is odd
+  // and p is the last pair) and has index kb * nk2 + p; it goes to A slot (index % NS).
+  const int nk2 = (nk + 1) >> 1;
+  const int T = nk * nkb, T2 = nk2 * nkb;
   const int a_col0 = acc_cols;
 
   if (warp < NPW) {
-    // ------------------------------------------------------------ halo loaders + A-stage builders
-    const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, stage image
+    // ------------------------------------------------------------ halo loaders + A-slot builders
+    const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, A slot
     const int r = q * 32 + lane;                    // this thread's tile row = TMEM lane
-    const uint32_t a_tm = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a_col0 + 32 * g);
-    const int c = tid & 7;                          // chunk this thread copies during halo loads
-    bool dirty = true;                              // the stage image holds data in some row of this warp
-    int it = g;
-    int ws = g;                                     // weight-ring slot of stage `it` (nw >= 4 = NS)
-    uint32_t wph = 0;
+    const uint32_t a_tm = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a_col0 + 64 * g);
+    bool dirty = true;                              // the slot holds data in some row of this warp
+    int v2 = g;                                     // next slot visit of this warp
     for (int kb = 0; kb < nkb; ++kb) {
       const int cvalid = min(32, Cin - kb * 32);    // live channels of this block (multiple of 8)
-      named_bar_sync(1, 32 * NPW);   // every builder has finished reading the previous channel block's halo
-      if (tid == 0) SCN_TL(32 + 2 * kb);
-      if (c * 4 < cvalid) {
-        const float *acol = A + kb * 32 + c * 4;
-        // chunk c of halo row h is stored at position (c + h) & 7, so that lanes reading the same chunk of different
-        // rows spread over the banks
-        for (int h = tid >> 3; h < hn; h += 4 * NPW)
-          cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)shids[h] * lda, 16u);
+      if (kb > 0) {
+        named_bar_sync(1, 32 * NPW);   // every builder has finished reading the previous channel block's halo
+        if (tid == 0) SCN_TL(32 + 2 * kb);
+        load_halo(kb);
+        cp_async_wait_all();
+        named_bar_sync(1, 32 * NPW);   // halo complete and visible to all builders
+        if (tid == 0) SCN_TL(33 + 2 * kb);
       }
-      cp_async_wait_all();
-      named_bar_sync(1, 32 * NPW);   // halo complete and visible to all builders
-      if (tid == 0) SCN_TL(33 + 2 * kb);
-      const int it_end = (kb + 1) * nk;
-      // Software pipeline: the first half of this warp's row of its NEXT stage is read from the halo into registers while
-      // the tensor pipe still owns the stage image (the whole row would not fit the 56-register budget of two CTAs per
-      // SM); the second half is fetched right after "slot free", under the first half's TMEM store.
-      float4 v0, v1, v2, v3;
-      uint32_t slot = kAbsent;
-      int k = 0;
+      const int v2_end = (kb + 1) * nk2;
+      // Software pipeline: the first 16 channels of the warp's NEXT visit are read from the halo into registers while the
+      // tensor pipe still owns the slot; the rest follows right after "slot free", under the first TMEM store.
+      float4 p0, p1, p2, p3;
+      uint32_t slot0 = kAbsent, slot1 = kAbsent;
+      int k0 = 0, k1 = 0;
       bool any = false;
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto load_half = [&](int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
+      auto load_half = [&](uint32_t slot, int k, int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
         a0 = a1 = a2 = a3 = z;
         if (slot < kOverflow) {
           const uint32_t rb = halo_base + slot * 128;
@@ -298,39 +327,56 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
           }
         }
       };
-      auto prefetch = [&](int it_) {
-        k = klist[it_ - kb * nk];
-        slot = slmap[k * kTile + r];
-        any = __any_sync(0xffffffffu, slot != kAbsent);
-        load_half(0, v0, v1, v2, v3);
+      auto prefetch = [&](int v2_) {
+        const int ki = 2 * (v2_ - kb * nk2);
+        k0 = klist[ki];
+        slot0 = slmap[k0 * kTile + r];
+        slot1 = kAbsent;
+        if (ki + 1 < nk) {
+          k1 = klist[ki + 1];
+          slot1 = slmap[k1 * kTile + r];
+        }
+        any = __any_sync(0xffffffffu, (slot0 & slot1) != kAbsent);
+        load_half(slot0, k0, 0, p0, p1, p2, p3);
       };
-      if (it < it_end) prefetch(it);
-      for (; it < it_end; it += NS) {
-        const uint32_t ph = (uint32_t)(it / NS) & 1u;
-        // quarter 0 also vouches for the stage's weight slice, so the MMA thread polls ONE barrier per stage
-        if (q == 0 && lane == 0) mbar_wait(wfull + ws, wph);
-        mbar_wait_sleep(empty + g, ph ^ 1u, 100);
+      if (v2 < v2_end) prefetch(v2);
+      for (; v2 < v2_end; v2 += NS) {
+        const int ki = 2 * (v2 - kb * nk2);
+        const bool two = ki + 1 < nk;
+        if (q == 0 && lane == 0) {
+          // quarter 0 also vouches for the visit's weight slices, so the MMA thread polls ONE barrier per visit
+          const int st = kb * nk + ki;
+          mbar_wait(wfull + st % nw, (uint32_t)(st / nw) & 1u);
+          if (two) mbar_wait(wfull + (st + 1) % nw, (uint32_t)((st + 1) / nw) & 1u);
+        }
+        mbar_wait(empty + g, ((uint32_t)(v2 / NS) & 1u) ^ 1u);
         tc_fence_after();
-        if (q == 0 && it / NS < 128) SCN_TL(64 + g * 256 + 2 * (it / NS));
+        if (q == 0 && v2 / NS < 128) SCN_TL(64 + g * 256 + 2 * (v2 / NS));
         if (any || dirty) {
+          float4 u0, u1, u2, u3;
           if (cvalid > 16) {
-            float4 u0, u1, u2, u3;
-            load_half(1, u0, u1, u2, u3);
-            tmem_st16(a_tm, v0, v1, v2, v3);
+            load_half(slot0, k0, 1, u0, u1, u2, u3);
+            tmem_st16(a_tm, p0, p1, p2, p3);
             tmem_st16(a_tm + 16, u0, u1, u2, u3);
           } else {
-            tmem_st16(a_tm, v0, v1, v2, v3);
+            tmem_st16(a_tm, p0, p1, p2, p3);
+          }
+          if (two) {
+            load_half(slot1, k1, 0, u0, u1, u2, u3);
+            tmem_st16(a_tm + 32, u0, u1, u2, u3);
+            if (cvalid > 16) {
+              load_half(slot1, k1, 1, u0, u1, u2, u3);
+              tmem_st16(a_tm + 48, u0, u1, u2, u3);
+            }
           }
           tmem_st_wait();
         }
-        dirty = any;
+        dirty = any || !two;   // (a one-stage visit leaves the slot's second half as it was)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full + g);
-        ws += NS;
-        if (ws >= nw) { ws -= nw; wph ^= 1u; }
-        if (q == 0 && it / NS < 128) SCN_TL(65 + g * 256 + 2 * (it / NS));
-        if (it + NS < it_end) prefetch(it + NS);
+        if (q == 0 && v2 / NS < 128) SCN_TL(65 + g * 256 + 2 * (v2 / NS));
+        if (v2 + NS < v2_end) prefetch(v2 + NS);
       }
     }
   } else if (warp == NPW + 1) {
@@ -351,42 +397,46 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   } else if (elect_one()) {
     // ------------------------------------------------------------ MMA issuer (one elected lane runs the whole loop)
     // This thread's dependent instruction chain paces the whole CTA (every instruction of it competes with ~9 warps for
-    // its scheduler), so the loop is kept minimal: stage index and phase are compile-time (unrolled by NS), descriptors
-    // advance by additions, one barrier wait per stage (the stage's quarter-0 builder vouches for the W slice).
+    // its scheduler), so the loop is kept minimal: descriptors advance by additions, one barrier wait and one commit
+    // per slot visit (8 MMAs).
     const uint64_t desc_hi = make_smem_desc(0, 16, 1024) & 0xFFFFFFFF00000000ull;
     const uint32_t b_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull) + (b_base >> 4);
     const uint32_t b_step = b_bytes >> 4;
     const uint32_t a_tm0 = tmem + (uint32_t)a_col0;
     const int wh = nw >> 1;
     const int nj_last = ((Cin - 1) & 31) + 1 >> 3;   // K = 8 steps of the last channel block (4 when Cin % 32 == 0)
-    const int it_last = (nkb - 1) * nk;              // first stage of the last channel block
-    int ws = 0;
+    int ws = 0, s = 0;
     uint32_t b_lo = b_lo0, ph = 0, accf = 0;
-    for (int it0 = 0; it0 < T; it0 += NS) {
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const int it = it0 + s;
-        if (it < T) {
-          mbar_wait(full + s, ph);   // A stage written AND its W slice landed
-          tc_fence_after();
-          const uint32_t a_tm = a_tm0 + 32 * s;
-          if (nj_last == 4 || it < it_last) {
-            mma_tf32_ts(tmem, a_tm, desc_hi | (uint64_t)b_lo, idesc, accf);
-            mma_tf32_ts(tmem, a_tm + 8, desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
-            mma_tf32_ts(tmem, a_tm + 16, desc_hi | (uint64_t)(b_lo + 4), idesc, 1u);
-            mma_tf32_ts(tmem, a_tm + 24, desc_hi | (uint64_t)(b_lo + 6), idesc, 1u);
-          } else {
-            for (int j = 0; j < nj_last; ++j)
-              mma_tf32_ts(tmem, a_tm + 8 * j, desc_hi | (uint64_t)(b_lo + 2 * j), idesc, j ? 1u : accf);
-          }
-          accf = 1u;
-          mma_commit(empty + s);
-          b_lo += b_step;
-          if (++ws == wh) mma_commit(wempty + 0);
-          else if (ws == nw) { mma_commit(wempty + 1); ws = 0; b_lo = b_lo0; }
-        }
+    auto stage = [&](uint32_t a_tm, int nj) {
+      if (nj == 4) {
+        mma_tf32_ts(tmem, a_tm, desc_hi | (uint64_t)b_lo, idesc, accf);
+        mma_tf32_ts(tmem, a_tm + 8, desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
+        mma_tf32_ts(tmem, a_tm + 16, desc_hi | (uint64_t)(b_lo + 4), idesc, 1u);
+        mma_tf32_ts(tmem, a_tm + 24, desc_hi | (uint64_t)(b_lo + 6), idesc, 1u);
+      } else {
+        for (int j = 0; j < nj; ++j)
+          mma_tf32_ts(tmem, a_tm + 8 * j, desc_hi | (uint64_t)(b_lo + 2 * j), idesc, j ? 1u : accf);
       }
-      ph ^= 1u;
+      accf = 1u;
+      b_lo += b_step;
+      if (++ws == wh) mma_commit(wempty + 0);
+      else if (ws == nw) { mma_commit(wempty + 1); ws = 0; b_lo = b_lo0; }
+    };
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int nj = kb == nkb - 1 ? nj_last : 4;
+      for (int p = 0; p < nk2; ++p) {
+        if (kb == 0 && p < 64) SCN_TL(1088 + 4 * p);
+        mbar_wait(full + s, ph);   // A slot written AND its W slices landed
+        tc_fence_after();
+        if (kb == 0 && p < 64) SCN_TL(1089 + 4 * p);
+        const uint32_t a_tm = a_tm0 + 64 * s;
+        stage(a_tm, nj);
+        if (2 * p + 1 < nk) stage(a_tm + 32, nj);
+        if (kb == 0 && p < 64) SCN_TL(1090 + 4 * p);
+        mma_commit(empty + s);
+        if (kb == 0 && p < 64) SCN_TL(1091 + 4 * p);
+        if (++s == NS) { s = 0; ph ^= 1u; }
+      }
     }
     mma_commit(accum);
   }
@@ -394,8 +444,8 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
 
   if (warp < NPW) {
     // ------------------------------------------------------------ epilogue: TMEM -> registers -> global
-    // warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows); the four warps of a lane quarter split the column chunks
-    if (T > 0) {
+    // warp w reads TMEM lanes 32*(w%4)..+31 (= tile rows); the NS warps of a lane quarter split the column chunks
+    if (T2 > 0) {
       mbar_wait_sleep(accum, 0, 1000);
       tc_fence_after();
     }
@@ -403,9 +453,9 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int q = warp & 3;
     const int row = sorow[q * 32 + lane];
-    for (int c0 = 16 * (warp >> 2); c0 < Cout; c0 += 16 * (NPW / 4)) {
+    for (int c0 = 16 * (warp >> 2); c0 < Cout; c0 += 16 * NS) {
       float v[16];
-      if (T > 0) {
+      if (T2 > 0) {
         tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       } else {
 #pragma unroll
@@ -435,20 +485,20 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   if (warp == NPW) tmem_dealloc<NT>(tmem);
 }
 
-template <uint32_t NT, int MINB>
+template <uint32_t NT, int NS, int MINB>
 static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, const float *A, int64_t lda,
                        const int32_t *nbr, const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids,
                        const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin,
                        int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k,
                        int w_row0, cudaStream_t st) {
-  auto kern = halo_conv_tc_kernel<NT, MINB>;
+  auto kern = halo_conv_tc_kernel<NT, NS, MINB>;
   SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
   if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
-  kern<<<(unsigned)tiles, 32 * (kHaloWarps + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask,
-                                                                hcap, (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc,
-                                                                L, nw, acc_cols, w_rows_per_k, w_row0);
+  kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
+                                                            (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,
+                                                            acc_cols, w_rows_per_k, w_row0);
   return 0;
 }
 
@@ -456,31 +506,34 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
                           const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
                           const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
                           int64_t ldo, int w_rows_per_k, int w_row0, cudaStream_t st) {
-  // TMEM: accumulator (Cout columns, rounded to 32) + four A stages of 32 columns.  Up to 256 columns two CTAs share an
-  // SM (one CTA's halo load, prologue and epilogue hide behind the other's stages) if shared memory allows it too; the
-  // weight ring takes whatever shared memory is left, up to kHaloMaxW slots.
+  // TMEM: accumulator (Cout columns, rounded to 32) + NS A slots of 64 columns.  Within 256 columns two CTAs share an SM
+  // (one CTA's halo load, prologue and epilogue hide behind the other's stages) if shared memory allows it too: three
+  // slots up to Cout = 64, two up to Cout = 128; wider layers run one CTA per SM with four slots.  The weight ring takes
+  // whatever shared memory is left, up to kHaloMaxW slots.
   const int acc_cols = (Cout + 31) & ~31;
-  const int a_cols = 32 * kHaloStages;
-  const int cols = acc_cols + a_cols;
   const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
-  auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 4 (one slot per A stage), <= kHaloMaxW
+  auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 4, <= kHaloMaxW
     int nw = kHaloMaxW;
     while (nw > 4 && halo_layout(nw, Cout, hcap).total > budget) nw -= 2;
     nw_out = nw;
     return halo_layout(nw, Cout, hcap).total <= budget;
   };
   int nw = 0;
-  bool two = cols <= 256 && fit(half, nw);
+  int ns = acc_cols <= 64 ? 3 : acc_cols <= 128 ? 2 : 4;
+  bool two = ns < 4 && fit(half, nw);
   if (const char *e = getenv("B200SCN_HALO_CTAS")) two = two && atoi(e) != 1;   // experiment hook
-  if (!two && !fit(whole, nw))
-    return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
+  if (!two) {
+    ns = 4;
+    if (!fit(whole, nw))
+      return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
+  }
   const HaloSmem L = halo_layout(nw, Cout, hcap);
   const int64_t tiles = ceil_div(n, kTile);
   int rc;
 #define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
-  if (two) rc = launch_halo<256, 2>(SCN_ARGS);
-  else if (cols <= 256) rc = launch_halo<256, 1>(SCN_ARGS);
-  else rc = launch_halo<512, 1>(SCN_ARGS);
+  if (two && ns == 3) rc = launch_halo<256, 3, 2>(SCN_ARGS);
+  else if (two) rc = launch_halo<256, 2, 2>(SCN_ARGS);
+  else rc = launch_halo<512, 4, 1>(SCN_ARGS);
 #undef SCN_ARGS
   if (rc) return rc;
   SCN_CHECK_LAUNCH("subm_conv_tiled");
@@ -513,7 +566,7 @@ int b200scn_morton_keys(const uint64_t *ukeys, int64_t n, uint64_t *mkeys, void 
 int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hcap, uint16_t *lmap,
                       int32_t *halo_ids, int32_t *halo_n, uint32_t *kmask, void *stream) {
   if (n <= 0) return 0;
-  if (hcap < 8 || hcap > 1024 || (hcap & 7)) return set_error("tile_plan: hcap=%d must be a multiple of 8 in [8,1024]", hcap);
+  if (hcap < 8 || hcap > 512 || (hcap & 7)) return set_error("tile_plan: hcap=%d must be a multiple of 8 in [8,512]", hcap);
   if (n >= ((int64_t)1 << 31)) return set_error("tile_plan: too many rows");
   if (reinterpret_cast<uintptr_t>(lmap) & 15) return set_error("tile_plan: lmap must be 16-byte aligned");
   const size_t smem = sizeof(int) * (kTileMap + kPlanHash) + sizeof(unsigned short) * kPlanHash;
@@ -534,10 +587,14 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
       (reinterpret_cast<uintptr_t>(Wkm) & 15))
     return set_error("subm_conv_tiled: needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 1024, 16-byte aligned rows "
                      "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
-  if (hcap < 8 || hcap > 1024 || (hcap & 7)) return set_error("subm_conv_tiled: bad hcap %d", hcap);
-  // output channels beyond 256 (the widest tcgen05 N) are produced by separate launches over column slices
-  for (int n0 = 0; n0 < Cout; n0 += 256) {
-    const int nc = Cout - n0 < 256 ? Cout - n0 : 256;
+  if (hcap < 8 || hcap > 512 || (hcap & 7)) return set_error("subm_conv_tiled: bad hcap %d", hcap);
+  // One launch covers up to 224 output channels; wider layers are produced by separate launches over equal column slices.
+  // (N = 256 with the A operand in TMEM gave wrong, run-to-run varying sums on B200 -- tools/halo_sweep.py -- while every
+  //  N <= 224 is bit-identical to the shared-memory-operand kernel, so the slice width stops at 224.)
+  const int nsl = (Cout + 223) / 224;
+  const int width = ((Cout + nsl - 1) / nsl + 15) & ~15;
+  for (int n0 = 0; n0 < Cout; n0 += width) {
+    const int nc = Cout - n0 < width ? Cout - n0 : width;
     if (halo_conv_part(A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, nc,
                        addend ? addend + n0 : nullptr, ldadd, out + n0, ldo, Cout, n0, (cudaStream_t)stream))
       return 1;

@@ -96,7 +96,7 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
  *   halo_ids[t*hcap + s]  the distinct neighbour ids the tile references (first hcap of them), halo_n[t] their number,
  *   lmap[t*3456 + k*128 + r]  halo slot of nbr[perm[128t+r]*27+k]; 0xFFFF absent, 0xFFFE beyond hcap (fetched through nbr),
  *   kmask[t]  bit k set iff offset k occurs in the tile.
- * hcap: multiple of 8 in [8,1024].  lmap must be 16-byte aligned and hold ceil(n/128)*3456 entries. */
+ * hcap: multiple of 8 in [8,512].  lmap must be 16-byte aligned and hold ceil(n/128)*3456 entries. */
 int b200scn_morton_keys(const uint64_t *ukeys, int64_t n, uint64_t *mkeys, void *stream);
 int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hcap, uint16_t *lmap,
                       int32_t *halo_ids, int32_t *halo_n, uint32_t *kmask, void *stream);
