@@ -184,7 +184,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
                     const uint16_t *__restrict__ lmap, const int32_t *__restrict__ halo_ids,
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
-                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int w_rows_per_k, int w_row0) {
+                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int pf_dist, int w_rows_per_k, int w_row0) {
   constexpr int NPW = 4 * NS;
   constexpr int NTHREADS = 32 * (NPW + 2);
   extern __shared__ uint8_t smem_raw[];
@@ -256,6 +256,18 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       fence_barrier_init();
       tma_prefetch_desc(&tmW);
     }
+  }
+  // L2 prefetch for the CTA that will run `pf_dist` tiles later (roughly one wave ahead, on whatever SM): its plan slice now,
+  // its first halo block once this CTA's builders are done (below).  A tile's prologue is two dependent global round trips
+  // (plan, then halo rows) that nothing inside the CTA can hide.
+  const int pf_tile = tile + pf_dist;
+  const bool pf_on = pf_dist > 0 && (int64_t)pf_tile * kTile < n_rows;
+  if (pf_on && warp < NPW) {
+    const char *pl = reinterpret_cast<const char *>(lmap + (int64_t)pf_tile * kTileMap);
+    const char *pi = reinterpret_cast<const char *>(halo_ids + (int64_t)pf_tile * hcap);
+    if (tid < kTileMap * 2 / 128) prefetch_l2(pl + tid * 128);
+    else if (tid < kTileMap * 2 / 128 + hcap * 4 / 128) prefetch_l2(pi + (tid - kTileMap * 2 / 128) * 128);
+    else if (tid < kTileMap * 2 / 128 + hcap * 4 / 128 + 4) prefetch_l2(perm + (int64_t)pf_tile * kTile + (tid - kTileMap * 2 / 128 - hcap * 4 / 128) * 32);
   }
   // halo of channel block kb: chunk c of halo row h is stored at position (c + h) & 7, so that lanes reading the same
   // chunk of different rows spread over the banks
@@ -353,6 +365,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         tc_fence_after();
         if (q == 0 && v2 / NS < 128) SCN_TL(64 + g * 256 + 2 * (v2 / NS));
         if (any || dirty) {
+          // (measured, no gain: a second register set so that the next half-row's reads fly under the previous TMEM store)
           float4 u0, u1, u2, u3;
           if (cvalid > 16) {
             load_half(slot0, k0, 1, u0, u1, u2, u3);
@@ -378,6 +391,12 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         if (q == 0 && v2 / NS < 128) SCN_TL(65 + g * 256 + 2 * (v2 / NS));
         if (v2 + NS < v2_end) prefetch(v2 + NS);
       }
+    }
+    // successor tile's first halo block -> L2 (its ids were prefetched at the start of this CTA and are L2 hits by now)
+    if (pf_on) {
+      const int hn2 = __ldg(halo_n + pf_tile);
+      const int32_t *ids = halo_ids + (int64_t)pf_tile * hcap;
+      for (int h = tid; h < hn2; h += 32 * NPW) prefetch_l2(A + (int64_t)__ldg(ids + h) * lda);
     }
   } else if (warp == NPW + 1) {
     // ------------------------------------------------------------ weight TMA (one thread)
@@ -496,9 +515,11 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
   if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
+  int pf_dist = kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
+  if (const char *e = getenv("B200SCN_HALO_PF")) pf_dist = atoi(e);   // experiment hook (0 = off)
   kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
                                                             (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,
-                                                            acc_cols, w_rows_per_k, w_row0);
+                                                            acc_cols, pf_dist, w_rows_per_k, w_row0);
   return 0;
 }
 
