@@ -250,8 +250,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         mbar_init(empty + s, 1);
       }
       for (int s = 0; s < nw; ++s) mbar_init(wfull + s, 1);   // the weight TMA's expect_tx arrival
-      mbar_init(wempty + 0, 1);    // the ring is released in two halves (one tcgen05.commit per half, not per slot)
-      mbar_init(wempty + 1, 1);
+      for (int s = 0; s < (nw >> 1); ++s) mbar_init(wempty + s, 1);   // the ring is released in pairs of slots
       mbar_init(accum, 1);
       fence_barrier_init();
       tma_prefetch_desc(&tmW);
@@ -401,12 +400,10 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   } else if (warp == NPW + 1) {
     // ------------------------------------------------------------ weight TMA (one thread)
     if (lane == 0) {
-      const int wh = nw >> 1;
       int s = 0, ki = 0, kb = 0;
       uint32_t ph = 0;
       for (int it = 0; it < T; ++it) {
-        if (s == 0) mbar_wait_sleep(wempty + 0, ph ^ 1u, 200);
-        else if (s == wh) mbar_wait_sleep(wempty + 1, ph ^ 1u, 200);
+        if ((s & 1) == 0) mbar_wait(wempty + (s >> 1), ph ^ 1u);   // pair (s, s+1) consumed by the tensor pipe
         mbar_arrive_expect_tx(wfull + s, b_bytes);
         tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, klist[ki] * w_rows_per_k + w_row0, wfull + s);
         if (++ki == nk) { ki = 0; ++kb; }
@@ -422,7 +419,6 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     const uint32_t b_lo0 = (uint32_t)(make_smem_desc(0, 16, 1024) & 0xFFFFFFFFull) + (b_base >> 4);
     const uint32_t b_step = b_bytes >> 4;
     const uint32_t a_tm0 = tmem + (uint32_t)a_col0;
-    const int wh = nw >> 1;
     const int nj_last = ((Cin - 1) & 31) + 1 >> 3;   // K = 8 steps of the last channel block (4 when Cin % 32 == 0)
     int ws = 0, s = 0;
     uint32_t b_lo = b_lo0, ph = 0, accf = 0;
@@ -438,8 +434,10 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       }
       accf = 1u;
       b_lo += b_step;
-      if (++ws == wh) mma_commit(wempty + 0);
-      else if (ws == nw) { mma_commit(wempty + 1); ws = 0; b_lo = b_lo0; }
+      if ((++ws & 1) == 0) {   // a pair of ring slots is released by one commit
+        mma_commit(wempty + (ws >> 1) - 1);
+        if (ws == nw) { ws = 0; b_lo = b_lo0; }
+      }
     };
     for (int kb = 0; kb < nkb; ++kb) {
       const int nj = kb == nkb - 1 ? nj_last : 4;
