@@ -436,10 +436,12 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k = blockIdx.y;
+  // offsets vary fastest over the grid: CTAs resident at the same time work on the same stretch of every offset's list,
+  // i.e. (with Morton-ordered lists) on the same region of space, so gathered rows are shared in L2
+  const int k = blockIdx.x;
   const int beg = offsets ? offsets[k] : 0;
   const int end = offsets ? offsets[k + 1] : n_single;
-  const int p0 = beg + blockIdx.x * chunk;
+  const int p0 = beg + blockIdx.y * chunk;
   const int p1 = min(p0 + chunk, end);
   if (p0 >= p1) return;  // uniform for the whole CTA
   const int T = (p1 - p0 + kDwPairs - 1) / kDwPairs;
@@ -582,9 +584,12 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
   int64_t want_chunks = ceil_div((int64_t)kNumSMs * 4, (int64_t)K);
   int64_t chunk = ceil_div(n_pairs_max, want_chunks > 0 ? want_chunks : 1);
   if (chunk < 512) chunk = 512;
-  if (chunk > 16384) chunk = 16384;
+  int64_t chunk_max = 4096;   // small chunks keep the region the resident CTAs work on (27 offsets x ~11 chunks) inside L2
+  if (const char *e = getenv("B200SCN_DW_CHUNK")) chunk_max = atoi(e) >= 512 ? atoi(e) : 512;   // experiment hook
+  if (chunk > chunk_max) chunk = chunk_max;
+  if (ceil_div(n_pairs_max, chunk) > 65535) chunk = ceil_div(n_pairs_max, 65535);
   chunk = ceil_div(chunk, kDwPairs) * kDwPairs;
-  dim3 grid((unsigned)ceil_div(n_pairs_max, chunk), (unsigned)K);
+  dim3 grid((unsigned)K, (unsigned)ceil_div(n_pairs_max, chunk));
   const uint32_t idesc = make_idesc_tf32(128, Cg, 1, 1);
   const int cols = mt * Cg;
 #define SCN_LAUNCH_DW(NT)                                                                                        \

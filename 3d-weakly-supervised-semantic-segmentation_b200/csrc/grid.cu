@@ -164,25 +164,29 @@ __global__ void __launch_bounds__(256) subm_map_kernel(const uint64_t *__restric
 }
 
 // ------------------------------------------------------------------------------------------ pair lists
+// `order` (optional): the list of offset k enumerates rows order[0], order[1], ... instead of 0, 1, ... -- the canonical
+// scn form (ascending row) is order == NULL; the weight-gradient kernel walks the rows along the Morton curve instead.
 struct PairLoader {
-  const int32_t *map;
+  const int32_t *map, *order;
   int64_t n;
   int K;
   __device__ int live(int nn) const { return nn; }
   __device__ int operator()(int64_t t) const {
     int64_t k = t / n, o = t - k * n;
-    return map[o * K + k] >= 0;
+    const int64_t r = order ? order[o] : o;
+    return map[r * K + k] >= 0;
   }
 };
 struct PairWriter {
-  const int32_t *map;
+  const int32_t *map, *order;
   int64_t n;
   int K;
   int32_t *pair_in, *pair_out, *offsets;
   __device__ void operator()(int64_t t, int flag, int pos) const {
     int64_t k = t / n, o = t - k * n;
     if (o == 0) offsets[k] = pos;
-    if (flag) { pair_in[pos] = map[o * K + k]; pair_out[pos] = (int32_t)o; }
+    const int64_t r = order ? order[o] : o;
+    if (flag) { pair_in[pos] = map[r * K + k]; pair_out[pos] = (int32_t)r; }
   }
 };
 
@@ -288,12 +292,18 @@ size_t b200scn_pair_scratch_bytes(int64_t n, int K) {
 
 int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, int32_t *pair_out,
                        int32_t *offsets_dev, void *scratch, size_t scratch_bytes, void *stream) {
+  return b200scn_pair_lists_ordered(map, nullptr, n, K, pair_in, pair_out, offsets_dev, scratch, scratch_bytes, stream);
+}
+
+int b200scn_pair_lists_ordered(const int32_t *map, const int32_t *order, int64_t n, int K, int32_t *pair_in,
+                               int32_t *pair_out, int32_t *offsets_dev, void *scratch, size_t scratch_bytes,
+                               void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (scratch_bytes < b200scn_pair_scratch_bytes(n, K)) return set_error("pair_lists: scratch too small");
   if (n * K >= (int64_t)1 << 31) return set_error("pair_lists: n*K overflows int32");
   if (n <= 0) { SCN_CUDA(cudaMemsetAsync(offsets_dev, 0, sizeof(int32_t) * (K + 1), st)); return 0; }
-  PairLoader ld{map, n, K};
-  PairWriter wr{map, n, K, pair_in, pair_out, offsets_dev};
+  PairLoader ld{map, order, n, K};
+  PairWriter wr{map, order, n, K, pair_in, pair_out, offsets_dev};
   return scan_flags(ld, wr, n * K, nullptr, (int32_t *)scratch, offsets_dev + K, st);
 }
 

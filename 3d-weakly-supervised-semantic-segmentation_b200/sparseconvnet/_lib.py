@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200scn_child_map": (_i32, [_vp, _vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "b200scn_pair_scratch_bytes": (_sz, [_i64, _i32]),
     "b200scn_pair_lists": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200scn_pair_lists_ordered": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200scn_gather_conv_tf32_ok": (_i32, [_i32, _i32, _i64]),
     "b200scn_gather_conv": (_i32, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
     "b200scn_morton_keys": (_i32, [_vp, _i64, _vp, _vp]),

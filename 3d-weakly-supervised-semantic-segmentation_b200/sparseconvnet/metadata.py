@@ -29,6 +29,7 @@ class Level:
         self.nbr = None           # (n,27) int32
         self.nbr_counts = None    # (27,) int32 device: rules per offset
         self.pairs = None         # (pair_in, pair_out, offsets_dev)
+        self.pairs_ordered = None
         self._counts = None
         self.plan = None          # TilePlan of the spatially tiled convolution
 
@@ -67,6 +68,13 @@ class Level:
             self.pairs = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()))
         return self.pairs
 
+    def subm_pairs_ordered(self, perm):
+        """The same pairs with every offset's list walking the sites along the Morton curve (weight gradient only:
+        CTAs that run at the same time then gather rows that are neighbours in space and hit in L2)."""
+        if self.pairs_ordered is None:
+            self.pairs_ordered = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()), order=perm)
+        return self.pairs_ordered
+
 
 class TilePlan:
     """perm (n,) int32 site ids along the Morton curve; lmap (T,27,128) uint16; halo_ids (T,hcap) int32; halo_n, kmask (T,)."""
@@ -90,8 +98,9 @@ class TilePlan:
                                     ptr(self.halo_n), ptr(self.kmask), st))
 
 
-def build_pairs(map_t, n, K, total):
-    """scn-form rulebook (per-offset (in,out) pair lists, ascending out) from a map[n][K] with `total` entries >= 0."""
+def build_pairs(map_t, n, K, total, order=None):
+    """scn-form rulebook (per-offset (in,out) pair lists, ascending out) from a map[n][K] with `total` entries >= 0.
+    `order`: optional int32 permutation of the rows replacing "ascending"."""
     dev = map_t.device
     offsets = torch.empty(K + 1, dtype=torch.int32, device=dev)
     nbytes = lib.b200scn_pair_scratch_bytes(n, K)
@@ -99,7 +108,8 @@ def build_pairs(map_t, n, K, total):
     pair_in = alloc_flat(max(total, 1), dev, torch.int32)
     pair_out = alloc_flat(max(total, 1), dev, torch.int32)
     st = _lib.stream_for(map_t)
-    check(lib.b200scn_pair_lists(ptr(map_t), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets), ptr(scratch), nbytes, st))
+    check(lib.b200scn_pair_lists_ordered(ptr(map_t), ptr(order), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets),
+                                         ptr(scratch), nbytes, st))
     return pair_in, pair_out, offsets
 
 

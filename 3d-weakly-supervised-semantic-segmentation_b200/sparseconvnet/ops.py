@@ -227,7 +227,10 @@ class SubmanifoldConvFn(torch.autograd.Function):
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
             dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True))
         if ctx.needs_input_grad[1]:
-            pin, pout, offs = level.subm_pairs()
+            if _precision[0] == 1 and _use_tiled(level.n):
+                pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
+            else:
+                pin, pout, offs = level.subm_pairs()
             dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
         return dx, dw, None
 

@@ -74,6 +74,12 @@ int b200scn_child_map(const int32_t *parent, const uint8_t *off, int64_t nf_max,
 size_t b200scn_pair_scratch_bytes(int64_t n, int K);
 int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, int32_t *pair_out,
                        int32_t *offsets_dev, void *scratch, size_t scratch_bytes, void *stream);
+/* Same lists with the rows of every offset enumerated in the order order[0], order[1], ... (a permutation of 0..n-1)
+ * instead of ascending: the same pairs, used by the weight gradient so that concurrently running CTAs touch rows that are
+ * neighbours in space (order = the Morton permutation of b200scn_tile_plan).  order NULL = the canonical form above. */
+int b200scn_pair_lists_ordered(const int32_t *map, const int32_t *order, int64_t n, int K, int32_t *pair_in,
+                               int32_t *pair_out, int32_t *offsets_dev, void *scratch, size_t scratch_bytes,
+                               void *stream);
 
 /* ------------------------------------------------------------------ convolutions (A5-A7, A10) */
 /* out[o,:] = sum_k A[map[o*K+k],:] . W[k]  (+ addend[o,:] if addend)      W: (K,Cin,Cout) row-major.
