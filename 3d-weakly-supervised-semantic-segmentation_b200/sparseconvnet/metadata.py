@@ -84,10 +84,12 @@ class TilePlan:
         dev = nbr.device
         n = level.n
         st = _lib.stream_for(nbr)
-        mk = alloc_flat(n, dev, torch.int64)
+        # curve keys live in a quantised-capacity buffer padded with +inf keys, so that the sort (torch's radix sort --
+        # plumbing) and its outputs have sizes that repeat from step to step (see _lib.round_rows) and padding sorts last
+        cap = _lib.round_rows(max(n, 1))
+        mk = torch.full((cap,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
         check(lib.b200scn_morton_keys(ptr(level.ukeys), n, ptr(mk), st))
-        # sorting the curve keys is plumbing (torch's radix sort); keys are unique, b < 2^15 keeps them positive
-        self.perm = torch.sort(mk)[1].to(torch.int32)
+        self.perm = torch.sort(mk)[1].to(torch.int32)[:n]   # keys are unique; b < 2^15 keeps them positive
         T = (n + 127) // 128
         self.hcap = hcap
         self.lmap = alloc_flat(T * 27 * 128, dev, torch.int16)

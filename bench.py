@@ -9,6 +9,7 @@ OutputLayer -> scalar loss (mean of the per-point outputs) -> full backward (inp
 summed over the batch and over ranks.  One JSON line on stdout (rank 0).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -44,6 +45,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
+        self.period = float(os.environ.get("B200SCN_NVML_PERIOD", "0.3"))
         self.t = threading.Thread(target=self._run, daemon=True)
         self.h = None
         try:
@@ -61,12 +63,14 @@ class ClockSampler:
         nv = self.nv
         while not self.stop:
             try:
+                t0 = time.perf_counter()
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.rows.append((sm, rs))
+                self.rows.append((sm, rs, time.perf_counter() - t0))
             except Exception:
                 pass
-            time.sleep(0.1)
+            # every query holds the driver lock for a few ms and stalls kernel launches, so sample sparsely
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.h is not None:
@@ -86,7 +90,8 @@ class ClockSampler:
         bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
         reasons = sorted(n for n, b in bits.items() if any(r[1] & b for r in self.rows))
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(sm),
+                "nvml_ms_per_sample": 1e3 * sum(r[2] for r in self.rows) / len(self.rows)}
 
 
 def _make_inputs(cfg, rank, n_distinct, n_points):
@@ -242,6 +247,9 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         stats["voxels"] = 0
+        # no cyclic-GC pass inside the timed steps (a generation-2 sweep over a step's object graph costs ~0.2 s of host time)
+        gc.collect()
+        gc.disable()
         launches0 = scn.launch_count()
         if prof:
             scn_ops.profile_reserve(800 * args.steps)
@@ -250,13 +258,16 @@ def run_b200(args):
         e0.record()
         for i in range(args.steps):
             loss = step(args.warmup + i, from_host)
-            if from_host:
-                loss_host = loss.item()  # D2H read of the step's result  # noqa: F841
+            # D2H read of the step's result, every step in both arms: a training loop logs its loss, and without it the
+            # host runs a step ahead, two steps' activations are alive at once and the caching allocator occasionally
+            # grows (cudaMalloc + implicit sync, ~0.1-0.2 s) inside the timed region
+            loss_host = loss.item()  # noqa: F841
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        gc.enable()
         ms = e0.elapsed_time(e1)
         prof_out = scn_ops.profile_end() if prof else None
         t = torch.tensor([ms, float(stats["voxels"])], dtype=torch.float64, device=dev)
@@ -270,11 +281,21 @@ def run_b200(args):
         return ms, vox, scn.launch_count() - launches0, prof_out
 
     # allocator priming (untimed, before any warm-up): site counts differ per batch, so torch's caching allocator needs to
-    # have met every distinct batch twice before its block pool stops growing (cudaMalloc inside a step synchronises)
-    for i in range(2 * n_distinct):
-        step(i, False)
-    torch.cuda.synchronize()
+    # have met every distinct batch before its block pool stops growing (cudaMalloc inside a step synchronises): whole
+    # cycles over the distinct batches until a cycle passes without a new cudaMalloc, at most 8 cycles.  The NVML sampler
+    # thread starts here too: its first queries take the driver lock for ~0.2 s, which must not land in a timed step.
     with ClockSampler(local) as clk:
+        mallocs = -1
+        for cycle in range(8):
+            for i in range(n_distinct):
+                step(i, False)
+                step(i, True)
+            torch.cuda.synchronize()
+            now = torch.cuda.memory_stats()["num_device_alloc"]
+            if cycle >= 1 and now == mallocs:
+                break
+            mallocs = now
+        clk.rows.clear()
         ms, vox, launches, _ = timed(False, False)         # headline: device-resident inputs, nothing but the step
     clocks = clk.summary()
     ms_e, vox_e, _, _ = timed(True, False)                 # end to end: pinned host inputs, H2D inside, loss read back
