@@ -287,18 +287,22 @@ gather_smallcin_kernel(const float *__restrict__ A, int64_t lda, const int32_t *
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t o = warp0; o < n_rows; o += nwarps) {
-    const int32_t *mrow = map ? map + o * K : nullptr;
-    int mine = (mrow && lane < K) ? __ldg(mrow + lane) : -1;   // K <= 32 entries of this row, one per lane
+    // lane k owns neighbour k: its index and its CI input values arrive in ONE dependent global round trip for the whole
+    // site (a per-neighbour loop of broadcast loads costs one round trip per present neighbour)
+    int mine = map ? (lane < K ? __ldg(map + o * K + lane) : -1) : (lane == 0 ? (int)o : -1);
+    float av[CI];
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) av[ci] = mine >= 0 ? __ldg(A + (int64_t)mine * lda + ci) : 0.f;
+    const unsigned present = __ballot_sync(0xffffffffu, mine >= 0);
     for (int c0 = 0; c0 < Cout; c0 += 32) {
       const int co = c0 + lane;
       float acc = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const int idx = mrow ? __shfl_sync(0xffffffffu, mine, k) : (int)o;
-        if (idx < 0) continue;  // warp-uniform
-        const float *a = A + (int64_t)idx * lda;
-        if (co < Cout) {
+      for (unsigned m = present; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
 #pragma unroll
-          for (int ci = 0; ci < CI; ++ci) acc = fmaf(__ldg(a + ci), sw[(k * CI + ci) * Cout + co], acc);
+        for (int ci = 0; ci < CI; ++ci) {
+          const float x = __shfl_sync(0xffffffffu, av[ci], k);
+          if (co < Cout) acc = fmaf(x, sw[(k * CI + ci) * Cout + co], acc);
         }
       }
       if (co < Cout) {
@@ -327,14 +331,28 @@ gather_smallcout_kernel(const float *__restrict__ A, int64_t lda, const int32_t 
     float acc[CO];
 #pragma unroll
     for (int j = 0; j < CO; ++j) acc[j] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const int idx = mrow ? __shfl_sync(0xffffffffu, mine, k) : (int)o;
-      if (idx < 0) continue;
-      const float *a = A + (int64_t)idx * lda;
-      for (int ci = lane; ci < Cin; ci += 32) {
-        const float x = __ldg(a + ci);
+    // present neighbours four at a time: their row loads are issued together (one round trip per four rows)
+    unsigned m = mrow ? __ballot_sync(0xffffffffu, mine >= 0) : 1u;
+    while (m) {
+      int kk[4], id[4];
 #pragma unroll
-        for (int j = 0; j < CO; ++j) acc[j] = fmaf(x, sw[(k * Cin + ci) * CO + j], acc[j]);
+      for (int u = 0; u < 4; ++u) {
+        kk[u] = m ? __ffs(m) - 1 : -1;
+        m &= m - 1;
+        const int sh = __shfl_sync(0xffffffffu, mine, kk[u] & 31);
+        id[u] = kk[u] < 0 ? -1 : (mrow ? sh : (int)o);
+      }
+      for (int ci = lane; ci < Cin; ci += 32) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = id[u] >= 0 ? __ldg(A + (int64_t)id[u] * lda + ci) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (id[u] >= 0) {
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc[j] = fmaf(x[u], sw[(kk[u] * Cin + ci) * CO + j], acc[j]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -461,6 +479,7 @@ int pair_dw_simt(const float *A, int64_t lda, const float *G, int64_t ldg, const
     int64_t want = ceil_div((int64_t)kNumSMs * 8, (int64_t)K);
     int64_t ch = ceil_div(n_pairs_max, want > 0 ? want : 1);
     if (ch < 256) ch = 256;
+    if (ch > 2048) ch = 2048;   // n_pairs_max only bounds the lists (most are ~10x shorter): small chunks keep every SM busy
     dim3 g((unsigned)ceil_div(n_pairs_max, ch), (unsigned)K);
     switch (Ca) {
       case 1: pair_dw_smallca_kernel<1><<<g, 256, 0, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, (int)ch, Cg, dW); break;
