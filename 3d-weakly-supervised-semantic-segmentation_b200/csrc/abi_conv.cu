@@ -81,3 +81,43 @@ extern "C" int b200scn_set_device(int device) {
   SCN_CUDA(cudaSetDevice(device));
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight preparation for the tensor-core kernels: one launch turns the parameter stack w0 (K, a, b) into the K-major
+// operand (K, Cout_g, Cin_g) of one GEMM direction -- offsets optionally mirrored (k -> K-1-k), matrices optionally
+// transposed -- and rounds every value to the nearest TF32 (cvt.rna; the tensor core itself would truncate the low 13
+// mantissa bits, a bias of up to 2^-10 per weight).
+namespace b200scn {
+__global__ void prep_weight_kernel(const float *__restrict__ w0, int K, int a, int b, int transposed, int flip,
+                                   float *__restrict__ out) {
+  // transposed == 0: GEMM multiplies by w0[k] (Cin = a, Cout = b): out[k][co][ci] = w0[kk][ci][co]
+  // transposed == 1: GEMM multiplies by w0[k]^T (Cin = b, Cout = a): out[k][co][ci] = w0[kk][co][ci]
+  const int64_t n = (int64_t)K * a * b;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e / ((int64_t)a * b));
+    const int r = (int)(e - (int64_t)k * a * b);
+    const int kk = flip ? K - 1 - k : k;
+    float v;
+    if (transposed) {
+      v = __ldg(w0 + (int64_t)kk * a * b + r);
+    } else {
+      const int co = r / a, ci = r - co * a;   // out is (b, a) row-major
+      v = __ldg(w0 + ((int64_t)kk * a + ci) * b + co);
+    }
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    out[e] = __uint_as_float(t);
+  }
+}
+}  // namespace b200scn
+
+extern "C" int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transposed, int flip, float *out,
+                                        void *stream) {
+  const int64_t n = (int64_t)K * a * b;
+  if (n <= 0) return 0;
+  const unsigned blocks = (unsigned)min((int64_t)kNumSMs * 8, ceil_div(n, 256));
+  prep_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w0, K, a, b, transposed, flip, out);
+  SCN_CHECK_LAUNCH("prep_weight_tf32");
+  count_launch(1);
+  return 0;
+}

@@ -525,10 +525,10 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
                           const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
                           const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
                           int64_t ldo, int w_rows_per_k, int w_row0, cudaStream_t st) {
-  // TMEM: accumulator (Cout columns, rounded to 32) + NS A slots of 64 columns.  Within 256 columns two CTAs share an SM
-  // (one CTA's halo load, prologue and epilogue hide behind the other's stages) if shared memory allows it too: three
-  // slots up to Cout = 64, two up to Cout = 128; wider layers run one CTA per SM with four slots.  The weight ring takes
-  // whatever shared memory is left, up to kHaloMaxW slots.
+  // TMEM: accumulator (Cout <= 128 columns, rounded to 32) + NS A slots of 64 columns = at most 256 columns, so that two
+  // CTAs share an SM (one CTA's halo load, prologue and epilogue hide behind the other's stages) when shared memory allows
+  // it too: three slots up to Cout = 64, two up to Cout = 128.  The weight ring takes whatever shared memory is left, up
+  // to kHaloMaxW slots; with a large halo capacity the same kernel simply runs one CTA per SM.
   const int acc_cols = (Cout + 31) & ~31;
   const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
   auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 4, <= kHaloMaxW
@@ -538,21 +538,16 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
     return halo_layout(nw, Cout, hcap).total <= budget;
   };
   int nw = 0;
-  int ns = acc_cols <= 64 ? 3 : acc_cols <= 128 ? 2 : 4;
-  bool two = ns < 4 && fit(half, nw);
+  bool two = fit(half, nw);
   if (const char *e = getenv("B200SCN_HALO_CTAS")) two = two && atoi(e) != 1;   // experiment hook
-  if (!two) {
-    ns = 4;
-    if (!fit(whole, nw))
-      return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
-  }
+  if (!two && !fit(whole, nw))
+    return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
   const HaloSmem L = halo_layout(nw, Cout, hcap);
   const int64_t tiles = ceil_div(n, kTile);
   int rc;
 #define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
-  if (two && ns == 3) rc = launch_halo<256, 3, 2>(SCN_ARGS);
-  else if (two) rc = launch_halo<256, 2, 2>(SCN_ARGS);
-  else rc = launch_halo<512, 4, 1>(SCN_ARGS);
+  if (acc_cols <= 64) rc = launch_halo<256, 3, 2>(SCN_ARGS);
+  else rc = launch_halo<256, 2, 2>(SCN_ARGS);
 #undef SCN_ARGS
   if (rc) return rc;
   SCN_CHECK_LAUNCH("subm_conv_tiled");
@@ -607,10 +602,11 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
     return set_error("subm_conv_tiled: needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 1024, 16-byte aligned rows "
                      "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
   if (hcap < 8 || hcap > 512 || (hcap & 7)) return set_error("subm_conv_tiled: bad hcap %d", hcap);
-  // One launch covers up to 224 output channels; wider layers are produced by separate launches over equal column slices.
-  // (N = 256 with the A operand in TMEM gave wrong, run-to-run varying sums on B200 -- tools/halo_sweep.py -- while every
-  //  N <= 224 is bit-identical to the shared-memory-operand kernel, so the slice width stops at 224.)
-  const int nsl = (Cout + 223) / 224;
+  // One launch covers up to 128 output channels (accumulator + A slots within 256 TMEM columns, two CTAs per SM); wider
+  // layers are produced by separate launches over equal column slices.  Two wider single-launch configurations were
+  // built and withdrawn: N = 256 mis-summed (run-to-run varying results, tools/halo_sweep.py), and a one-CTA-per-SM
+  // four-slot configuration for 160..224 channels showed rare run-to-run mismatches when a CTA owned one channel block.
+  const int nsl = (Cout + 127) / 128;
   const int width = ((Cout + nsl - 1) / nsl + 15) & ~15;
   for (int n0 = 0; n0 < Cout; n0 += width) {
     const int nc = Cout - n0 < width ? Cout - n0 : width;

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200scn_morton_keys": (_i32, [_vp, _i64, _vp, _vp]),
     "b200scn_tile_plan": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200scn_subm_conv_tiled": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "b200scn_prep_weight_tf32": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200scn_scatter_conv": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),

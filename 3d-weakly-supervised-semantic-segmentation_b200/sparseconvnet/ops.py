@@ -112,9 +112,13 @@ class GemmWeight:
         w = self._base()
         return (w.transpose(1, 2) if self.transposed else w).contiguous()
 
-    def kmajor(self):     # (K,Cout_g,Cin_g)
-        w = self._base()
-        return (w if self.transposed else w.transpose(1, 2)).contiguous()
+    def kmajor(self):     # (K,Cout_g,Cin_g), rounded to the nearest TF32, one launch
+        w0 = self.w0.contiguous()
+        K, a, b = w0.shape
+        out = torch.empty((K, self.cout, self.cin), dtype=torch.float32, device=w0.device)
+        check(lib.b200scn_prep_weight_tf32(ptr(w0), K, a, b, 1 if self.transposed else 0, 1 if self.flip else 0,
+                                           ptr(out), _lib.stream_for(w0)))
+        return out
 
 
 def _use_tf32(gw, lda, x):
@@ -122,7 +126,8 @@ def _use_tf32(gw, lda, x):
 
 
 # Spatially tiled submanifold convolution (conv_halo.cu): halo capacity per 128-row tile and the smallest level it is
-# used for (below that the gather kernel's offset-split variant wins; B200SCN_HALO=1 forces it on, =0 off).
+# used for (below that the step is bound by host launch overhead, not by the kernel); B200SCN_HALO=1 forces it on for every
+# size, =0 off.
 _halo = {"hcap": int(os.environ.get("B200SCN_HALO_CAP", "384")), "min_rows": 128 * 148}
 
 

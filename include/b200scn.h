@@ -112,6 +112,11 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
                             const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
                             const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream);
 
+/* K-major TF32 operand of one GEMM direction from the parameter stack w0 (K,a,b) in one launch: offsets mirrored if flip,
+ * matrices transposed unless `transposed` (transposed = 0: multiply by w0[k], out (K,b,a); = 1: by w0[k]^T, out (K,a,b)),
+ * values rounded to the nearest TF32 (the tensor core would truncate).  Input of every precision = 1 entry point. */
+int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transposed, int flip, float *out, void *stream);
+
 /* out[map[j*K+k],:] = A[j,:] . W[k] for every present (j,k)   (Deconvolution_updateOutput,
  * Convolution backward-input).  Rows of `out` not addressed by map are left untouched. */
 int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,
