@@ -311,9 +311,10 @@ def run_b200(args):
             g = prof["gather27"]
             ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full
-            # capture (profiles/r1_final_ncu_gather_details.txt): the level-1 64->64 SubmanifoldConvolution forward of
-            # this workload, whose algorithmic bytes are 241.8 MB -- no re-read beyond the compulsory traffic.
-            traffic = {"bytes": 228.6e6, "launch": "level-1 SubM 64->64 fwd, 411829 sites", "algorithmic_bytes": 241.8e6}
+            # capture (profiles/r1_halo_ncu_details.txt): the level-1 64->64 SubmanifoldConvolution forward of this
+            # workload (tiled kernel), 135.2 MB read + 64.5 MB written against 241.8 MB algorithmic -- no re-read beyond the
+            # compulsory traffic (part of the input is still L2-resident from the producing kernel).
+            traffic = {"bytes": 199.6e6, "launch": "level-1 SubM 64->64 fwd, 411829 sites", "algorithmic_bytes": 241.8e6}
             roof = {"bound": "hbm", "kernel": g["kernel"], "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic["bytes"], "traffic_detail": traffic, "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / g["n"],
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "tflops": g["flops"] / (g["ms"] * 1e-3) / 1e12,
