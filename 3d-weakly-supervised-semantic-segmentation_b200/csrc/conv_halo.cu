@@ -9,8 +9,9 @@
 //   plan (once per level and step):  sites sorted along a Morton curve (perm), cut into 128-row tiles; per tile the set
 //        of distinct neighbour ids ("halo", <= hcap slots) and a local map lmap[k][r] = halo slot of nbr[perm[r]][k];
 //   conv (every layer, fwd and bwd-input): per 32-channel block the tile's halo rows are copied global -> shared ONCE
-//        (cp.async, the only L2 latency left), then the 27 per-offset A operands are assembled shared -> shared into the
-//        SWIZZLE_128B stage images tcgen05.mma reads; W slices by TMA; accumulator in TMEM; each output row written once.
+//        (cp.async, the only L2 latency left), then for every kernel offset the builder warps read their rows from the halo
+//        and write them with tcgen05.st into TENSOR MEMORY, where tcgen05.mma reads its A operand; W slices by TMA into a
+//        shared-memory ring; accumulator in TMEM; each output row written once.
 // Slots beyond hcap (0xFFFE in lmap) are fetched from global through the ordinary neighbour map, so any input is handled.
 #include <stdlib.h>
 
@@ -68,6 +69,20 @@ tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ pe
     int id = -1;
     if (row < n) id = __ldg(nbr + (int64_t)__ldg(perm + row) * 27 + k);
     ids[k * kTile + r] = id;
+  }
+  __syncthreads();
+  // The tile's own rows (every site is its own neighbour at the centre offset 13) take halo slots 0..rows-1 in tile order:
+  // the builders of the convolution kernel read 8 consecutive tile rows per shared-memory wavefront, and a row's bank
+  // group is its slot modulo 8, so the centre offset -- and every offset whose neighbours are again consecutive tile rows
+  // -- is read without bank conflicts; it also makes the slot order deterministic for these rows.
+  if (tid < kTile) {
+    const int id = ids[13 * kTile + tid];
+    if (id >= 0) {
+      uint32_t h = ((uint32_t)id * 2654435761u) >> 19;
+      while (atomicCAS(hk + h, -1, id) != -1) h = (h + 1) & (kPlanHash - 1);   // own rows are distinct
+      hv[h] = (unsigned short)tid;
+    }
+    if (tid == 0) cnt = min(kTile, n - row0);
   }
   __syncthreads();
   for (int e = tid; e < kTileMap; e += kPlanThreads) {   // whole warps: kTileMap and kPlanThreads are multiples of 32
@@ -156,7 +171,7 @@ static HaloSmem halo_layout(int nw, int Cout, int hcap) {
   HaloSmem L;
   L.b_off = 0;
   L.halo_off = L.b_off + (uint32_t)nw * Cout * 128;
-  L.lmap_off = L.halo_off + (uint32_t)hcap * 128;
+  L.lmap_off = L.halo_off + ((uint32_t)hcap + 1) * 128;   // + one all-zero row that absent neighbours read
   L.orow_off = L.lmap_off + ((kTileMap * 2 + 15) & ~15);
   L.hids_off = L.orow_off + kTile * 4;
   L.klist_off = L.hids_off + (((uint32_t)hcap * 4 + 15) & ~15u);
@@ -239,6 +254,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       }
     }
     if (tid < kTile) sorow[tid] = row0 + tid < n_rows ? __ldg(perm + row0 + tid) : -1;
+    if (tid < 8) sts_f4(halo_base + (uint32_t)hcap * 128 + tid * 16, make_float4(0.f, 0.f, 0.f, 0.f));
     if (tid == 0) {
       const uint32_t km = __ldg(kmask + tile);
       int n = 0;
@@ -318,18 +334,19 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       uint32_t slot0 = kAbsent, slot1 = kAbsent;
       int k0 = 0, k1 = 0;
       bool any = false;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      // Branch-free: absent neighbours read the all-zero row (halo row `hcap`, one broadcast address); rows beyond the halo
+      // capacity read it too and are then fetched through the global neighbour map under a warp-uniform test (rare).
+      bool ovf = false;
       auto load_half = [&](uint32_t slot, int k, int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
-        a0 = a1 = a2 = a3 = z;
-        if (slot < kOverflow) {
-          const uint32_t rb = halo_base + slot * 128;
-          a0 = lds_f4(rb + (((slot + 4 * hf + 0) & 7u) << 4));
-          a1 = lds_f4(rb + (((slot + 4 * hf + 1) & 7u) << 4));
-          a2 = lds_f4(rb + (((slot + 4 * hf + 2) & 7u) << 4));
-          a3 = lds_f4(rb + (((slot + 4 * hf + 3) & 7u) << 4));
-        } else if (slot == kOverflow) {   // beyond the halo capacity: through the global neighbour map
+        const uint32_t rowi = slot < kOverflow ? slot : (uint32_t)hcap;
+        const uint32_t rb = halo_base + rowi * 128;
+        a0 = lds_f4(rb + (((rowi + 4 * hf + 0) & 7u) << 4));
+        a1 = lds_f4(rb + (((rowi + 4 * hf + 1) & 7u) << 4));
+        a2 = lds_f4(rb + (((rowi + 4 * hf + 2) & 7u) << 4));
+        a3 = lds_f4(rb + (((rowi + 4 * hf + 3) & 7u) << 4));
+        if (ovf && slot == kOverflow) {
           const int idx = __ldg(nbr + (int64_t)sorow[r] * 27 + k);
-          const float *src = A + (int64_t)idx * lda + kb * 32 + hf * 16;
+          const float *src = A + (int64_t)idx * lda + (kb * 32 + hf * 16);
           a0 = ldg_f4(src);
           a1 = ldg_f4(src + 4);
           if (hf * 16 + 8 < cvalid) {
@@ -348,6 +365,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
           slot1 = slmap[k1 * kTile + r];
         }
         any = __any_sync(0xffffffffu, (slot0 & slot1) != kAbsent);
+        ovf = __any_sync(0xffffffffu, slot0 == kOverflow || slot1 == kOverflow);
         load_half(slot0, k0, 0, p0, p1, p2, p3);
       };
       if (v2 < v2_end) prefetch(v2);
@@ -381,7 +399,9 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
               tmem_st16(a_tm + 48, u0, u1, u2, u3);
             }
           }
+          if (q == 0 && v2 / NS < 128) SCN_TL(2200 + g * 512 + 4 * (v2 / NS));
           tmem_st_wait();
+          if (q == 0 && v2 / NS < 128) SCN_TL(2201 + g * 512 + 4 * (v2 / NS));
         }
         dirty = any || !two;   // (a one-stage visit leaves the slot's second half as it was)
         tc_fence_before();

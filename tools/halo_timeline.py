@@ -30,6 +30,9 @@ for kb in range((cin + 31) // 32): print("halo kb", kb, "start", r(32 + 2 * kb),
 for g in range(4):
     rows = [(r(64 + g * 256 + 2 * u), r(65 + g * 256 + 2 * u)) for u in range(128) if t[64 + g * 256 + 2 * u]]
     if rows: print("builder group", g, " (slot free, built):", rows[:30])
+for g in range(3):
+    rows = [(r(64 + g * 256 + 2 * u), r(2200 + g * 512 + 4 * u), r(2201 + g * 512 + 4 * u), r(65 + g * 256 + 2 * u)) for u in range(6) if t[2200 + g * 512 + 4 * u]]
+    if rows: print("builder", g, "(slot free, stores issued, stores done, arrived):", rows)
 mm = [(r(1088 + 4 * i), r(1089 + 4 * i), r(1090 + 4 * i), r(1091 + 4 * i)) for i in range(64) if t[1088 + 4 * i]]
 print("mma visits (wait begins, operands seen, mmas issued, committed):", mm[:40])
 print("mma (after mmas, after commit1):", [(r(1600 + 2 * i), r(1601 + 2 * i)) for i in range(128) if t[1600 + 2 * i]][:60])
