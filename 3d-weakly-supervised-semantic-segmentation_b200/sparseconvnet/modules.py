@@ -73,14 +73,48 @@ def _check3(dimension):
         raise NotImplementedError("b200scn implements dimension 3 only (the reference uses 3 everywhere)")
 
 
+# Residual blocks (scn.UNet / FullyConvolutionalNet with residual_blocks=True) are ConcatTable(skip, Sequential(..., conv))
+# followed by AddTable.  With fusion on (default) Sequential.forward recognises that pair and lets the last convolution
+# add the skip branch in its epilogue (one read of the addend instead of a separate read-read-write pass); the module
+# tree, parameter names and results are unchanged.
+_fuse_residual = [True]
+
+
+def set_fusion(on):
+    _fuse_residual[0] = bool(on)
+
+
+def _fusable_residual(m, nxt):
+    if not (_fuse_residual[0] and type(m) is ConcatTable and type(nxt) is AddTable and len(m._modules) == 2):
+        return False
+    branch = m._modules["1"]
+    if type(branch) is not Sequential or len(branch._modules) == 0:
+        return False
+    last = list(branch._modules.values())[-1]
+    return type(last) is SubmanifoldConvolution and last.bias is None
+
+
 class Sequential(torch.nn.Sequential):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
         return self
 
     def forward(self, input):
-        for module in self._modules.values():
-            input = module(input)
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if i + 1 < len(mods) and _fusable_residual(m, mods[i + 1]):
+                skip = m._modules["0"](input)
+                branch = list(m._modules["1"]._modules.values())
+                y = input
+                for mod in branch[:-1]:
+                    y = mod(y)
+                input = branch[-1](y, addend=skip.features)
+                i += 2
+                continue
+            input = m(input)
+            i += 1
         return input
 
     def input_spatial_size(self, out_size):
@@ -204,10 +238,11 @@ class SubmanifoldConvolution(_ConvBase):
             raise NotImplementedError("SubmanifoldConvolution: filter_size 3 only (the reference uses 3)")
         self._init_weight(dimension, nIn, nOut, filter_size, bias, groups)
 
-    def forward(self, input):
+    def forward(self, input, addend=None):
+        """addend: optional (N, nOut) features added to the result in the kernel's epilogue (fused residual add)."""
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, self.nOut, input)
         level = input.metadata.levels[_size(input)]
-        feats = ops.SubmanifoldConvFn.apply(input.features, self._w(), level)
+        feats = ops.SubmanifoldConvFn.apply(input.features, self._w(), level, addend)
         return self._finish(input, feats, input.spatial_size, level)
 
     def input_spatial_size(self, out_size):

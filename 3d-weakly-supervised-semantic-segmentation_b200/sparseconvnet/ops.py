@@ -218,10 +218,10 @@ class SubmanifoldConvFn(torch.autograd.Function):
     SubmanifoldConvolution_updateOutput / _backward."""
 
     @staticmethod
-    def forward(ctx, x, w, level):
+    def forward(ctx, x, w, level, addend=None):
         ctx.level = level
         ctx.save_for_backward(x, w)
-        return subm_conv(x, level, GemmWeight(w))
+        return subm_conv(x, level, GemmWeight(w), addend=addend)
 
     @staticmethod
     def backward(ctx, g):
@@ -237,7 +237,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
             else:
                 pin, pout, offs = level.subm_pairs()
             dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
-        return dx, dw, None
+        return dx, dw, None, (g if ctx.needs_input_grad[3] else None)
 
 
 class ConvolutionFn(torch.autograd.Function):

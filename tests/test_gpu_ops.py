@@ -139,3 +139,18 @@ def test_output_layer_and_counters():
     _check(mg, mr, xg, xr, fg, fr, dense_out=True)
     assert scn.forward_pass_multiplyAdd_count == ref.forward_pass_multiplyAdd_count
     assert scn.forward_pass_hidden_states == ref.forward_pass_hidden_states
+
+
+def test_weight_preparation():
+    """b200scn_prep_weight_tf32: K-major operand of both GEMM directions, values rounded to the nearest TF32."""
+    from sparseconvnet.ops import GemmWeight
+    torch.manual_seed(3)
+    w = torch.randn(27, 5, 7, device="cuda")
+
+    def tf32(t):   # round to nearest, ties away from zero, 10 mantissa bits kept
+        return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    f = GemmWeight(w)
+    assert torch.equal(f.kmajor(), tf32(w.transpose(1, 2).contiguous()))
+    b = GemmWeight(w, transposed=True, flip=True)
+    assert torch.equal(b.kmajor(), tf32(w.flip(0).contiguous()))
+    assert float((f.kmajor() - w.transpose(1, 2)).abs().max() / w.abs().max()) < 2 ** -11

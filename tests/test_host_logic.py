@@ -87,11 +87,10 @@ def test_gemm_weight_forms():
     f = GemmWeight(w)
     assert (f.cin, f.cout) == (5, 7)
     assert torch.allclose(x @ f.rowmajor()[3], x @ w[3])
-    assert torch.allclose(f.kmajor()[3], w[3].t())
     b = GemmWeight(w, transposed=True, flip=True)
     assert (b.cin, b.cout) == (7, 5)
     assert torch.allclose(g @ b.rowmajor()[3], g @ w[23].t())
-    assert torch.allclose(b.kmajor()[3], w[23])
+    # the K-major tensor-core form is produced by a CUDA kernel: tests/test_gpu_ops.py::test_weight_preparation
 
 
 def test_capacity_rounding_and_scene_generator():
