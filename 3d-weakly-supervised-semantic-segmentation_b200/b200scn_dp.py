@@ -1,40 +1,99 @@
 """Scene-sharded data parallelism: one process per GPU, each rank builds its own rulebooks for its own
-scenes; the only exchange is one fp32 gradient all-reduce (mean) per step over NCCL / NVLink, between
-loss.backward() and optimizer.step() (train.py:80-81).  The reference has no distributed code at all; BatchNorm
-statistics stay per rank, as independent scn replicas would behave.
+scenes; the only exchange is the fp32 gradient all-reduce (mean) of every step over NCCL, between loss.backward() and
+optimizer.step() (train.py:80-81).  The reference has no distributed code at all; BatchNorm statistics stay per rank,
+as independent scn replicas would behave.
 """
 import torch
 import torch.distributed as dist
 
 
 class FlatGrads:
-    """The step's single exchange: every parameter gradient is packed into ONE flat fp32 buffer (one multi-tensor copy),
-    all-reduced once -- sized for launch latency, not one collective per tensor -- and unpacked in place.
+    """The step's single exchange.  Every parameter gradient has a slot in ONE flat fp32 buffer, cut into a few buckets
+    (reverse parameter order = the order backward produces them).  A post-accumulate hook per parameter counts a bucket
+    down; the moment a bucket is complete its gradients are packed with one multi-tensor copy and its all-reduce starts
+    asynchronously, so the transfer runs under the rest of the backward pass -- measured on 2 B200s of one box the
+    un-overlapped 120 MB all-reduce cost 14 ms of a 58 ms step.  `allreduce_mean()` (after backward) reduces whatever is
+    still pending, waits, scales and unpacks in place.
     (Gradients are NOT kept as views of the flat buffer: autograd would then add into them, one extra kernel per
     parameter and step.)"""
 
-    def __init__(self, params):
+    def __init__(self, params, bucket_bytes=16 << 20, group=None):
         self.params = [p for p in params if p.requires_grad]
         self.sizes = [p.numel() for p in self.params]
         self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
         self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+        self.group = group
+        # buckets: contiguous parameter ranges, filled from the LAST parameter backwards
+        self.buckets = []          # (first_param, last_param_exclusive, flat_begin, flat_end)
+        hi, acc = len(self.params), 0
+        ends = [0]
+        for s in self.sizes:
+            ends.append(ends[-1] + s)
+        for i in range(len(self.params) - 1, -1, -1):
+            acc += self.sizes[i] * 4
+            if acc >= bucket_bytes or i == 0:
+                self.buckets.append((i, hi, ends[i], ends[hi]))
+                hi, acc = i, 0
+        self.bucket_of = {}
+        for b, (lo, hi_, _, _) in enumerate(self.buckets):
+            for i in range(lo, hi_):
+                self.bucket_of[i] = b
+        self._pending = None       # per bucket: parameters still missing this step
+        self._works = []
+        self._launched = []
+        self._hooks = []
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
 
+    # ------------------------------------------------------------------ per step
     def zero(self):
         for p in self.params:
             p.grad = None
+        self._pending = [hi - lo for lo, hi, _, _ in self.buckets]
+        self._works = []
+        self._launched = [False] * len(self.buckets)
+
+    def _make_hook(self, i):
+        def hook(_p):
+            if self._pending is None:
+                return
+            b = self.bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        lo, hi, f0, f1 = self.buckets[b]
+        grads = [self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i])
+                 for i in range(lo, hi)]
+        for i, g in zip(range(lo, hi), grads):
+            if self.params[i].grad is None:
+                self.params[i].grad = g
+        torch._foreach_copy_(self.views[lo:hi], grads)
+        self._works.append(dist.all_reduce(self.flat[f0:f1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._launched[b] = True
 
     def allreduce_mean(self, group=None):
-        world = dist.get_world_size(group)
+        world = dist.get_world_size(self.group if group is None else group)
         if world <= 1:
             return
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self.views, grads)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if self._pending is None:          # zero() was not called this step: everything is still to do
+            self.zero_state_only()
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:      # parameters without a gradient this step, or hooks not registered
+                self._launch(b)
+        for w in self._works:
+            w.wait()
         self.flat.div_(world)
-        for p, g in zip(self.params, grads):
-            if p.grad is None:
-                p.grad = g
-        torch._foreach_copy_(grads, self.views)
+        torch._foreach_copy_([p.grad for p in self.params], self.views)
+        self._pending = None
+
+    def zero_state_only(self):
+        self._pending = [hi - lo for lo, hi, _, _ in self.buckets]
+        self._works = []
+        self._launched = [False] * len(self.buckets)
 
 
 def shard_scenes(n_scenes, rank, world):

@@ -24,7 +24,7 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 # site counts differ a little every step (fresh coordinates); rounding torch's own allocations keeps block sizes repeating
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8,expandable_segments:True")
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")
 import torch  # noqa: E402
 
 METRIC = "voxels/sec fwd+bwd SparseConvUNet m=32 2cm"
@@ -282,8 +282,8 @@ def run_b200(args):
 
     # allocator priming (untimed, before any warm-up): site counts differ per batch, so torch's caching allocator needs to
     # have met every distinct batch before its block pool stops growing (cudaMalloc inside a step synchronises): whole
-    # cycles over the distinct batches (at least four) until a cycle passes without a new cudaMalloc, at most 8 cycles;
-    # expandable segments (PYTORCH_CUDA_ALLOC_CONF above) let the pool grow by mapping pages instead of cudaMalloc.  The NVML sampler
+    # cycles over the distinct batches (at least four) until a cycle passes without a new cudaMalloc, at most 8 cycles.
+    # (expandable_segments was tried and made step times erratic: 46-106 ms.)  The NVML sampler
     # thread starts here too: its first queries take the driver lock for ~0.2 s, which must not land in a timed step.
     with ClockSampler(local) as clk:
         mallocs = -1

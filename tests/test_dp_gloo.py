@@ -19,13 +19,19 @@ def _worker(rank, world, port, out):
     from b200scn_dp import FlatGrads, shard_scenes
     torch.manual_seed(0)                       # identical initial weights on every rank
     net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
-    flat = FlatGrads(net.parameters())
+    # 8-byte buckets: every parameter is its own bucket, reduced asynchronously from its gradient hook during backward
+    flat = FlatGrads(net.parameters(), bucket_bytes=8)
+    assert len(flat.buckets) == 4 and flat.buckets[0][1] == 4 and flat.buckets[-1][0] == 0
     scenes = shard_scenes(5, rank, world)      # rank 0: 0,2,4   rank 1: 1,3
     torch.manual_seed(100 + rank)
     x = torch.randn(4 * len(scenes), 6)
     flat.zero()
+    local_parts = {}
+    for i, p in enumerate(net.parameters()):   # capture the local gradient before the in-flight reduction touches it
+        p.register_hook(lambda g, i=i: local_parts.__setitem__(i, g.detach().clone().reshape(-1)))
     net(x).pow(2).mean().backward()
-    local = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+    assert all(flat._launched)                 # every bucket's all-reduce was started by a hook, inside backward
+    local = torch.cat([local_parts[i] for i in range(4)])
     flat.allreduce_mean()
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
