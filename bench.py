@@ -45,7 +45,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], False
-        self.period = float(os.environ.get("B200SCN_NVML_PERIOD", "0.3"))
+        self.period = float(os.environ.get("B200SCN_NVML_PERIOD", "0.4"))
         self.t = threading.Thread(target=self._run, daemon=True)
         self.h = None
         try:
@@ -69,7 +69,8 @@ class ClockSampler:
                 self.rows.append((sm, rs, time.perf_counter() - t0))
             except Exception:
                 pass
-            # every query holds the driver lock for a few ms and stalls kernel launches, so sample sparsely
+            # every query holds the driver lock and stalls kernel launches (measured ~15 ms of step time per sample),
+            # so sample sparsely: two or three samples inside a 20-step timed region
             time.sleep(self.period)
 
     def __enter__(self):
