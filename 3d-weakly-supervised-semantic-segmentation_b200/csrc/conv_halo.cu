@@ -121,12 +121,15 @@ tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ pe
 }
 
 // ------------------------------------------------------------------------------------------------ convolution
-// Measured on B200 (tools/halo_timeline.py): with BOTH operands in shared memory a tcgen05.mma kind::tf32 of M = 128,
-// K = 8 costs ~120 cycles whatever N is (the A rows are fetched from shared memory at about one 128-byte swizzle row per
-// cycle), i.e. ~270 MAC/cycle/SM = 13 % of the TF32 peak at N = 32..64 -- that, not the gathers, bounded every earlier
-// variant.  Here the A operand lives in TENSOR MEMORY: a builder warp reads its 32 rows of the tile from the halo
-// (shared memory -> registers) and writes them with tcgen05.st straight into the TMEM lanes the MMA reads (lane = tile
-// row, one column per tf32 element); only the small W slice is a shared-memory operand.
+// Measured on B200 (tools/micro/mma_issue_bench.cu, kind::tf32, M = 128, K = 8; profiles/r1_mma_issue_microbench.txt):
+//  * issued from an `if (lane == 0)` region, or with one elect.sync per instruction, a tcgen05.mma costs ~100-120 cycles
+//    of scalar->uniform register moves and votes on the issuing thread whatever N and the operand source are;
+//  * issued in a loop that ONE elect.sync-chosen lane runs on its own it costs 55 / 69 / 97 / 160 cycles for N = 32 / 64 /
+//    128 / 256 with A in shared memory, and 16.5 / 32.3 / 64.0 / 127.4 (= N/2, the tensor pipe's real rate) with A in
+//    TENSOR MEMORY.
+// So here the A operand lives in TMEM: a builder warp reads its 32 rows of the tile from the halo (shared memory ->
+// registers) and writes them with tcgen05.st straight into the TMEM lanes the MMA reads (lane = tile row, one column per
+// tf32 element); only the small W slice is a shared-memory operand, and one elected lane runs the whole issue loop.
 constexpr int kHaloMaxSlots = 4;   // A slots in TMEM (64 columns = two stages of 32 channels each)
 constexpr int kHaloMaxW = 16;    // weight-ring slots
 
@@ -158,11 +161,6 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
-// One lane of a converged warp, chosen by elect.sync.  Measured on B200 (tools/micro/mma_issue_bench.cu, kind::tf32, M = 128,
-// K = 8, A in TMEM): issued from an `if (lane == 0)` region, or with one elect.sync per instruction, a tcgen05.mma costs
-// ~100 cycles of scalar->uniform register moves and votes on the issuing thread whatever N is; issued in a loop that one
-// elected lane runs on its own it costs N/2 cycles (16.5 / 32.3 / 64.0 / 127.4 for N = 32 / 64 / 128 / 256) -- the
-// tensor pipe's real rate.  With A in shared memory the same loop needs 55 / 69 / 97 / 160 cycles.  (elect_one: tc_common.cuh)
 struct HaloSmem {
   uint32_t b_off, halo_off, lmap_off, orow_off, hids_off, klist_off, bar_off, total;
 };
