@@ -232,3 +232,93 @@ int b200scn_output_features_bwd_csr(const float *d_out, int64_t n_sites, int C, 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Head pooling (SparseConvBase_.postProcessing, models/SparseConvNet.py:20-26, and
+// models/MultiLabelContrastive.py:35-40 -- a Python loop of torch.mean over out_feats[batch_offsets[i]:batch_offsets[i+1]]).
+// The per-point tensor only exists to be averaged per scene, and OutputLayer copies a voxel's row to each of its points, so
+//   pooled[b][c] = (1 / P_b) * sum over voxels v of scene b of  w(v) * feats[v][c],   w(v) = points in v (modes 3, 4) or 1
+// never needs the (sum P, C) tensor.  Level-0 ids are contiguous per scene (first occurrence in input row order, scenes
+// concatenated), so a block walking consecutive rows flushes its partial sums once per scene change.
+namespace b200scn {
+
+constexpr int kPoolRows = 256;
+
+__global__ void __launch_bounds__(128)
+scene_pool_kernel(const float *__restrict__ feats, int64_t ldf, const uint64_t *__restrict__ ukeys,
+                  const int32_t *__restrict__ count, int mode, int64_t n, int C, float *__restrict__ sums,
+                  float *__restrict__ npts) {
+  const int64_t r0 = (int64_t)blockIdx.x * kPoolRows, r1 = min(n, r0 + kPoolRows);
+  for (int c0 = 0; c0 < C; c0 += 128) {
+    const int c = c0 + threadIdx.x;
+    float acc = 0.f, pts = 0.f;
+    int cur = r0 < r1 ? (int)(__ldg(ukeys + r0) >> 48) : 0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int b = (int)(__ldg(ukeys + r) >> 48);
+      if (b != cur) {   // block-uniform
+        if (c < C) atomicAdd(sums + (int64_t)cur * C + c, acc);
+        if (c == 0) atomicAdd(npts + cur, pts);
+        acc = 0.f; pts = 0.f; cur = b;
+      }
+      const float cnt = (float)__ldg(count + r);
+      const float w = mode >= 3 ? cnt : 1.f;
+      if (c < C) acc = fmaf(w, __ldg(feats + r * ldf + c), acc);
+      pts += cnt;
+    }
+    if (r0 < r1) {
+      if (c < C) atomicAdd(sums + (int64_t)cur * C + c, acc);
+      if (c == 0) atomicAdd(npts + cur, pts);
+    }
+  }
+}
+
+__global__ void scene_pool_finish_kernel(float *__restrict__ sums, const float *__restrict__ npts, int B, int C) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * C) return;
+  const float p = npts[t / C];
+  sums[t] = p > 0.f ? sums[t] / p : 0.f;
+}
+
+__global__ void scene_pool_bwd_kernel(const float *__restrict__ g, const uint64_t *__restrict__ ukeys,
+                                      const int32_t *__restrict__ count, int mode, const float *__restrict__ npts,
+                                      int64_t n, int C, float *__restrict__ d_feats, int64_t ldd) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  const int64_t r = t / C;
+  const int c = (int)(t - r * C);
+  const int b = (int)(__ldg(ukeys + r) >> 48);
+  const float w = mode >= 3 ? (float)__ldg(count + r) : 1.f;
+  d_feats[r * ldd + c] = w * __ldg(g + (int64_t)b * C + c) / __ldg(npts + b);
+}
+
+}  // namespace b200scn
+
+extern "C" {
+
+int b200scn_scene_mean(const float *feats, int64_t ldf, const uint64_t *ukeys, const int32_t *count, int mode,
+                       int64_t n, int C, int B, float *out, float *npts, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B <= 0 || C <= 0) return set_error("scene_mean: bad sizes B=%d C=%d", B, C);
+  SCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C, st));
+  SCN_CUDA(cudaMemsetAsync(npts, 0, sizeof(float) * (size_t)B, st));
+  if (n > 0) {
+    // npts is accumulated once per channel chunk by thread 0 of the first chunk only (c == 0 exists in chunk c0 == 0)
+    scene_pool_kernel<<<(unsigned)ceil_div(n, kPoolRows), 128, 0, st>>>(feats, ldf, ukeys, count, mode, n, C, out, npts);
+    scene_pool_finish_kernel<<<(unsigned)ceil_div((int64_t)B * C, 256), 256, 0, st>>>(out, npts, B, C);
+    SCN_CHECK_LAUNCH("scene_mean");
+    count_launch(2);
+  }
+  return 0;
+}
+
+int b200scn_scene_mean_bwd(const float *g, const uint64_t *ukeys, const int32_t *count, int mode, const float *npts,
+                           int64_t n, int C, float *d_feats, int64_t ldd, void *stream) {
+  if (n <= 0) return 0;
+  scene_pool_bwd_kernel<<<(unsigned)ceil_div(n * C, 256), 256, 0, (cudaStream_t)stream>>>(g, ukeys, count, mode, npts, n, C,
+                                                                                         d_feats, ldd);
+  SCN_CHECK_LAUNCH("scene_mean_bwd");
+  count_launch(1);
+  return 0;
+}
+
+}  // extern "C"

@@ -201,6 +201,21 @@ class OutputLayer(Module):
         return out_size
 
 
+class SceneMeanPooling(Module):
+    """OutputLayer followed by the per-scene mean over points that the reference's heads take
+    (SparseConvBase_.postProcessing, models/SparseConvNet.py:20-26; models/MultiLabelContrastive.py:35-40), as one fused
+    op on the level-0 voxel features: forward(x[, batch_size]) -> (B, C).  Not part of upstream scn: an optional
+    replacement for `OutputLayer` + the Python loop of torch.mean when only the pooled features are needed."""
+
+    def forward(self, input, batch_size=None):
+        md = input.metadata
+        level = md.levels[_size(input)]
+        if md.count is None or md.count.shape[0] != input.features.shape[0]:
+            raise ValueError("SceneMeanPooling needs the level-0 (InputLayer resolution) tensor")
+        B = int(batch_size) if batch_size is not None else input.batch_size()
+        return ops.SceneMeanFn.apply(input.features, md, level, B)
+
+
 class _ConvBase(Module):
     def _init_weight(self, dimension, nIn, nOut, filter_size, bias, groups):
         _check3(dimension)

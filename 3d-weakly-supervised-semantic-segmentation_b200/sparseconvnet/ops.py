@@ -419,3 +419,30 @@ class OutputFeaturesFn(torch.autograd.Function):
                                                   ptr(md.first_row), ptr(md.last_row), md.mode, ptr(d), C,
                                                   _lib.stream_for(g)))
         return d, None
+
+
+class SceneMeanFn(torch.autograd.Function):
+    """Per-scene mean of the per-point features (SparseConvBase_.postProcessing, models/SparseConvNet.py:20-26) straight
+    from the level-0 voxel features: OutputLayer + the Python loop of torch.mean without the (sum P, C) tensor."""
+
+    @staticmethod
+    def forward(ctx, feats, md, level, batch_size):
+        feats, ldf = _c(feats)
+        n, C = feats.shape
+        out = torch.empty((batch_size, C), dtype=torch.float32, device=feats.device)
+        npts = torch.empty(batch_size, dtype=torch.float32, device=feats.device)
+        check(lib.b200scn_scene_mean(ptr(feats), ldf, ptr(level.ukeys), ptr(md.count), md.mode, n, C, batch_size,
+                                     ptr(out), ptr(npts), _lib.stream_for(feats)))
+        ctx.md, ctx.level, ctx.n = md, level, n
+        ctx.save_for_backward(npts)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        npts, = ctx.saved_tensors
+        g = g.contiguous()
+        C = g.shape[1]
+        d = alloc_rows(ctx.n, C, g.device)
+        check(lib.b200scn_scene_mean_bwd(ptr(g), ptr(ctx.level.ukeys), ptr(ctx.md.count), ctx.md.mode, ptr(npts), ctx.n, C,
+                                         ptr(d), C, _lib.stream_for(g)))
+        return d, None, None, None

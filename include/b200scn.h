@@ -179,6 +179,15 @@ int b200scn_output_features_bwd_csr(const float *d_out, int64_t n_sites, int C, 
                                     const int32_t *count, const int32_t *rows, const int32_t *first_row,
                                     const int32_t *last_row, int mode, float *d_feats, int64_t ldf, void *stream);
 
+/* Head pooling (A11: SparseConvBase_.postProcessing, models/SparseConvNet.py:20-26; MultiLabelContrastive.py:35-40):
+ * out[b,:] = mean over the POINTS of scene b of the OutputLayer result, computed from the level-0 voxel features without
+ * materialising the per-point tensor: (1/P_b) sum_v w(v) feats[v,:], w(v) = count[v] (modes 3,4) or 1 (modes 1,2).
+ * ukeys/count: level-0 site keys (scene = key >> 48) and points per site; npts[B] receives P_b (kept for the backward). */
+int b200scn_scene_mean(const float *feats, int64_t ldf, const uint64_t *ukeys, const int32_t *count, int mode,
+                       int64_t n, int C, int B, float *out, float *npts, void *stream);
+int b200scn_scene_mean_bwd(const float *g, const uint64_t *ukeys, const int32_t *count, int mode, const float *npts,
+                           int64_t n, int C, float *d_feats, int64_t ldd, void *stream);
+
 /* ------------------------------------------------------------------ point2mask (A12) */
 /* ops/point2mask/_ext_src/src/ball_query.cpp:8-33 (+ ball_query_gpu.cu:9-45). idx is fully written
  * (-1 sentinel included). */

@@ -154,3 +154,27 @@ def test_weight_preparation():
     b = GemmWeight(w, transposed=True, flip=True)
     assert torch.equal(b.kmajor(), tf32(w.flip(0).contiguous()))
     assert float((f.kmajor() - w.transpose(1, 2)).abs().max() / w.abs().max()) < 2 ** -11
+
+
+@pytest.mark.parametrize("mode,c", [(4, 32), (3, 448), (2, 7)])
+def test_scene_mean_pooling(mode, c):
+    """A11: fused OutputLayer + per-scene mean over points == the reference's Python loop of torch.mean over
+    out_feats[batch_offsets[i]:batch_offsets[i+1]] (models/SparseConvNet.py:20-26), forward and gradient."""
+    import sparseconvnet as scn
+    coords, _ = random_cloud(11 + mode, 4000, 20, 3, dup_frac=0.5)
+    torch.manual_seed(mode)
+    f = torch.randn(coords.shape[0], c)
+    fa = f.clone().cuda().requires_grad_(True)
+    fb = f.clone().cuda().requires_grad_(True)
+    xa = scn.InputLayer(3, 4096, mode=mode)([coords, fa])
+    xb = scn.InputLayer(3, 4096, mode=mode)([coords, fb])
+    pooled = scn.SceneMeanPooling()(xa, batch_size=3)
+    per_point = scn.OutputLayer(3)(xb)
+    offs = [0, 4000, 8000, 12000]
+    want = torch.stack([per_point[offs[i]:offs[i + 1]].mean(0) for i in range(3)])
+    assert pooled.shape == (3, c)
+    assert rel_err(pooled, want) < 1e-5
+    go = torch.randn_like(want)
+    pooled.backward(go)
+    want.backward(go)
+    assert rel_err(fa.grad, fb.grad) < 1e-5
