@@ -322,3 +322,95 @@ int b200scn_scene_mean_bwd(const float *g, const uint64_t *ukeys, const int32_t 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// scn.MaxPooling (size == stride) and scn.SparseToDense (models/projector/components.py:78-100,
+// Function_test.py:46,87,203): adjacent scn ops on the rulebooks that already exist.
+namespace b200scn {
+
+// out[j][c] = max(0, max_k in[child[j][k]][c])   (upstream zero-initialises the output and takes the running maximum)
+__global__ void maxpool_kernel(const float *__restrict__ in, int64_t ldi, const int32_t *__restrict__ child,
+                               int64_t n_coarse, int K, int C, float *__restrict__ out, int64_t ldo) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_coarse * C) return;
+  const int64_t j = t / C;
+  const int c = (int)(t - j * C);
+  float m = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int i = __ldg(child + j * K + k);
+    if (i >= 0) m = fmaxf(m, __ldg(in + (int64_t)i * ldi + c));
+  }
+  out[j * ldo + c] = m;
+}
+
+// d_in[i][c] = g[parent[i]][c] where in[i][c] equals the pooled value (ties all receive it), else 0
+__global__ void maxpool_bwd_kernel(const float *__restrict__ g, int64_t ldg, const float *__restrict__ in, int64_t ldi,
+                                   const float *__restrict__ out, int64_t ldo, const int32_t *__restrict__ parent,
+                                   int64_t n_fine, int C, float *__restrict__ d_in, int64_t ldd) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_fine * C) return;
+  const int64_t i = t / C;
+  const int c = (int)(t - i * C);
+  const int64_t j = __ldg(parent + i);
+  d_in[i * ldd + c] = __ldg(in + i * ldi + c) == __ldg(out + j * ldo + c) ? __ldg(g + j * ldg + c) : 0.f;
+}
+
+// dense (B, C, S, S, S): scatter == 1: dense[b][c][x][y][z] = feats[v][c]; scatter == 0: feats[v][c] = dense[...] (backward)
+__global__ void sparse_dense_kernel(float *__restrict__ feats, int64_t ldf, const uint64_t *__restrict__ ukeys, int64_t n,
+                                    int C, int64_t S, float *__restrict__ dense, int scatter) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  const int64_t v = t / C;
+  const int c = (int)(t - v * C);
+  int x, y, z, b;
+  split_key(__ldg(ukeys + v), x, y, z, b);
+  const int64_t at = ((((int64_t)b * C + c) * S + x) * S + y) * S + z;
+  if (scatter) dense[at] = feats[v * ldf + c];
+  else feats[v * ldf + c] = dense[at];
+}
+
+}  // namespace b200scn
+
+extern "C" {
+
+int b200scn_maxpool(const float *in, int64_t ldi, const int32_t *child, int64_t n_coarse, int K, int C, float *out,
+                    int64_t ldo, void *stream) {
+  if (n_coarse <= 0) return 0;
+  maxpool_kernel<<<(unsigned)ceil_div(n_coarse * C, 256), 256, 0, (cudaStream_t)stream>>>(in, ldi, child, n_coarse, K, C,
+                                                                                          out, ldo);
+  SCN_CHECK_LAUNCH("maxpool");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_maxpool_bwd(const float *g, int64_t ldg, const float *in, int64_t ldi, const float *out, int64_t ldo,
+                        const int32_t *parent, int64_t n_fine, int C, float *d_in, int64_t ldd, void *stream) {
+  if (n_fine <= 0) return 0;
+  maxpool_bwd_kernel<<<(unsigned)ceil_div(n_fine * C, 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, in, ldi, out, ldo,
+                                                                                           parent, n_fine, C, d_in, ldd);
+  SCN_CHECK_LAUNCH("maxpool_bwd");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_sparse_to_dense(const float *feats, int64_t ldf, const uint64_t *ukeys, int64_t n, int C, int64_t spatial_size,
+                            float *dense, void *stream) {
+  if (n <= 0) return 0;
+  sparse_dense_kernel<<<(unsigned)ceil_div(n * C, 256), 256, 0, (cudaStream_t)stream>>>(const_cast<float *>(feats), ldf,
+                                                                                       ukeys, n, C, spatial_size, dense, 1);
+  SCN_CHECK_LAUNCH("sparse_to_dense");
+  count_launch(1);
+  return 0;
+}
+
+int b200scn_sparse_to_dense_bwd(const float *d_dense, const uint64_t *ukeys, int64_t n, int C, int64_t spatial_size,
+                                float *d_feats, int64_t ldf, void *stream) {
+  if (n <= 0) return 0;
+  sparse_dense_kernel<<<(unsigned)ceil_div(n * C, 256), 256, 0, (cudaStream_t)stream>>>(d_feats, ldf, ukeys, n, C, spatial_size,
+                                                                                       const_cast<float *>(d_dense), 0);
+  SCN_CHECK_LAUNCH("sparse_to_dense_bwd");
+  count_launch(1);
+  return 0;
+}
+
+}  // extern "C"

@@ -13,7 +13,7 @@ from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNor
                       Deconvolution, Identity, InputLayer, JoinTable, NetworkInNetwork, OutputLayer, Sequential,
                       SparseConvNetTensor, SubmanifoldConvolution, UnPooling)
 from .networks import FullyConvolutionalNet, UNet
-from .modules import SceneMeanPooling, set_fusion  # noqa: F401
+from .modules import MaxPooling, SceneMeanPooling, SparseToDense, set_fusion  # noqa: F401
 from .ops import get_precision, set_precision
 from .utils import checkpoint_restore, checkpoint_save, is_power2
 

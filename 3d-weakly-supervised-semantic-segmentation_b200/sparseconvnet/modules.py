@@ -336,6 +336,49 @@ class UnPooling(Module):
         return (out_size - self.pool_size) // self.pool_stride + 1
 
 
+class MaxPooling(Module):
+    """scn.MaxPooling(dimension, pool_size, pool_stride, nFeaturesToDrop=0), pool_size == pool_stride
+    (models/projector/components.py:78-100)."""
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        Module.__init__(self)
+        _check3(dimension)
+        if int(pool_size) != int(pool_stride):
+            raise NotImplementedError("MaxPooling: pool_size == pool_stride only")
+        if nFeaturesToDrop:
+            raise NotImplementedError("MaxPooling: nFeaturesToDrop != 0")
+        self.pool_size, self.pool_stride = int(pool_size), int(pool_stride)
+
+    def forward(self, input):
+        s = self.pool_size
+        size = _size(input)
+        csize = (size - s) // s + 1
+        assert (csize - 1) * s + s == size, "spatial size %d not compatible with size/stride %d" % (size, s)
+        down = input.metadata.get_down(size, s)
+        out = SparseConvNetTensor(None, input.metadata, torch.LongTensor([csize] * 3))
+        out.features = ops.MaxPoolingFn.apply(input.features, down)
+        return out
+
+    def input_spatial_size(self, out_size):
+        return (out_size - 1) * self.pool_stride + self.pool_size
+
+
+class SparseToDense(Module):
+    """scn.SparseToDense(dimension, nPlanes): (N, C) features -> dense (B, C, S, S, S) (Function_test.py:46)."""
+
+    def __init__(self, dimension, nPlanes):
+        Module.__init__(self)
+        _check3(dimension)
+        self.nPlanes = nPlanes
+
+    def forward(self, input):
+        level = input.metadata.levels[_size(input)]
+        return ops.SparseToDenseFn.apply(input.features, level, input.batch_size())
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
 class NetworkInNetwork(Module):
     def __init__(self, nIn, nOut, bias):
         Module.__init__(self)

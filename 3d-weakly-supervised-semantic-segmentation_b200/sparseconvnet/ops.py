@@ -446,3 +446,53 @@ class SceneMeanFn(torch.autograd.Function):
         check(lib.b200scn_scene_mean_bwd(ptr(g), ptr(ctx.level.ukeys), ptr(ctx.md.count), ctx.md.mode, ptr(npts), ctx.n, C,
                                          ptr(d), C, _lib.stream_for(g)))
         return d, None, None, None
+
+
+class MaxPoolingFn(torch.autograd.Function):
+    """scn.MaxPooling, size == stride (models/projector/components.py:78-100): MaxPooling_updateOutput / _updateGradInput."""
+
+    @staticmethod
+    def forward(ctx, x, down):
+        x, ldx = _c(x)
+        C = x.shape[1]
+        out = alloc_rows(down.coarse.n, C, x.device)
+        check(lib.b200scn_maxpool(ptr(x), ldx, ptr(down.child_map()), down.coarse.n, down.K, C, ptr(out), C,
+                                  _lib.stream_for(x)))
+        ctx.down = down
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out = ctx.saved_tensors
+        down = ctx.down
+        x, ldx = _c(x)
+        g, ldg = _c(g)
+        C = x.shape[1]
+        d = alloc_rows(down.fine.n, C, x.device)
+        check(lib.b200scn_maxpool_bwd(ptr(g), ldg, ptr(x), ldx, ptr(out), C, ptr(down.parent), down.fine.n, C, ptr(d), C,
+                                      _lib.stream_for(x)))
+        return d, None
+
+
+class SparseToDenseFn(torch.autograd.Function):
+    """scn.SparseToDense (Function_test.py:46): SparseToDense_updateOutput / _updateGradInput."""
+
+    @staticmethod
+    def forward(ctx, x, level, batch_size):
+        x, ldx = _c(x)
+        n, C = x.shape
+        S = level.size
+        dense = torch.zeros((batch_size, C, S, S, S), dtype=torch.float32, device=x.device)
+        check(lib.b200scn_sparse_to_dense(ptr(x), ldx, ptr(level.ukeys), n, C, S, ptr(dense), _lib.stream_for(x)))
+        ctx.level, ctx.n = level, n
+        return dense
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        C = g.shape[1]
+        d = alloc_rows(ctx.n, C, g.device)
+        check(lib.b200scn_sparse_to_dense_bwd(ptr(g), ptr(ctx.level.ukeys), ctx.n, C, ctx.level.size, ptr(d), C,
+                                              _lib.stream_for(g)))
+        return d, None, None

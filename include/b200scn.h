@@ -188,6 +188,20 @@ int b200scn_scene_mean(const float *feats, int64_t ldf, const uint64_t *ukeys, c
 int b200scn_scene_mean_bwd(const float *g, const uint64_t *ukeys, const int32_t *count, int mode, const float *npts,
                            int64_t n, int C, float *d_feats, int64_t ldd, void *stream);
 
+/* scn.MaxPooling with size == stride (MaxPooling_updateOutput / _updateGradInput; models/projector/components.py:78-100):
+ * out[j,:] = max(0, max over children of in[child,:]) -- upstream zero-initialises the output; the gradient goes to every
+ * child that equals the pooled value. */
+int b200scn_maxpool(const float *in, int64_t ldi, const int32_t *child, int64_t n_coarse, int K, int C, float *out,
+                    int64_t ldo, void *stream);
+int b200scn_maxpool_bwd(const float *g, int64_t ldg, const float *in, int64_t ldi, const float *out, int64_t ldo,
+                        const int32_t *parent, int64_t n_fine, int C, float *d_in, int64_t ldd, void *stream);
+/* scn.SparseToDense (SparseToDense_updateOutput / _updateGradInput; Function_test.py:46): dense is (B, C, S, S, S),
+ * zero-filled by the caller; the backward gathers d_feats[v,:] from d_dense. */
+int b200scn_sparse_to_dense(const float *feats, int64_t ldf, const uint64_t *ukeys, int64_t n, int C, int64_t spatial_size,
+                            float *dense, void *stream);
+int b200scn_sparse_to_dense_bwd(const float *d_dense, const uint64_t *ukeys, int64_t n, int C, int64_t spatial_size,
+                                float *d_feats, int64_t ldf, void *stream);
+
 /* ------------------------------------------------------------------ point2mask (A12) */
 /* ops/point2mask/_ext_src/src/ball_query.cpp:8-33 (+ ball_query_gpu.cu:9-45). idx is fully written
  * (-1 sentinel included). */

@@ -178,3 +178,28 @@ def test_scene_mean_pooling(mode, c):
     pooled.backward(go)
     want.backward(go)
     assert rel_err(fa.grad, fb.grad) < 1e-5
+
+
+def test_maxpooling_and_sparse_to_dense():
+    """scn.MaxPooling (size == stride) and scn.SparseToDense against the oracle, forward and gradient."""
+    coords, feats = random_cloud(21, 3000, 16, 2)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, 12)
+    mg = scn.Sequential(scn.MaxPooling(3, 2, 2), scn.SubmanifoldConvolution(3, 12, 8, 3, False))
+    mr = ref.Sequential(ref.MaxPooling(3, 2, 2), ref.SubmanifoldConvolution(3, 12, 8, 3, False))
+    _check(mg, mr, xg, xr, fg, fr)
+    # SparseToDense on a small spatial size (dense 64^3 volumes)
+    c = coords.clone()
+    for b in range(2):                      # every sample's cloud into the corner of a 64^3 volume
+        sel = c[:, 3] == b
+        c[sel, :3] = c[sel, :3] - c[sel, :3].min(0)[0]
+    f = torch.randn(c.shape[0], 5)
+    fg2 = f.clone().cuda().requires_grad_(True)
+    fr2 = f.clone().requires_grad_(True)
+    dg = scn.SparseToDense(3, 5)(scn.InputLayer(3, 64, mode=4)([c, fg2]))
+    dr = ref.SparseToDense(3, 5)(ref.InputLayer(3, 64, mode=4)([c, fr2]))
+    assert dg.shape == dr.shape == (2, 5, 64, 64, 64)
+    assert rel_err(dg, dr) < 1e-6
+    go = torch.randn_like(dr)
+    dg.backward(go.cuda())
+    dr.backward(go)
+    assert rel_err(fg2.grad, fr2.grad) < 1e-6
