@@ -155,7 +155,7 @@ def subm_conv(x, level, gw, addend=None):
     if addend is not None:
         addend, lda = _c(addend)
     w = gw.kmajor()
-    tok = _p0("gather27", "subm_conv_tiled", 4.0 * (x.shape[0] * Cin + level.n * Cout) + 4.0 * 27 * Cin * Cout,
+    tok = _p0("tiled27", "subm_conv_tiled", 4.0 * (x.shape[0] * Cin + level.n * Cout) + 4.0 * 27 * Cin * Cout,
               level, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_subm_conv_tiled(ptr(x), ldx, ptr(level.nbr), ptr(plan.perm), ptr(plan.lmap), ptr(plan.halo_ids),
                                       ptr(plan.halo_n), ptr(plan.kmask), plan.hcap, level.n, ptr(w), Cin, Cout,

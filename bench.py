@@ -309,8 +309,10 @@ def run_b200(args):
         peak, which = _peaks()
         h2d = sum(c.numel() * 8 + f.numel() * 4 for c, f in pinned) / len(pinned)
         roof = None
-        if prof and prof.get("gather27"):
-            g = prof["gather27"]
+        # the dominant kernel: the tiled submanifold kernel ("tiled27") wherever it runs, else the gather kernel
+        dom = max((k for k in ("tiled27", "gather27") if prof and prof.get(k)), key=lambda k: prof[k]["ms"], default=None)
+        if dom:
+            g = prof[dom]
             ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full
             # capture (profiles/r1_halo_ncu_details.txt): the level-1 64->64 SubmanifoldConvolution forward of this
