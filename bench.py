@@ -14,7 +14,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,12 +40,13 @@ def _peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons during the timed region, read in-process through NVML (the same counters as the
-    nvidia-smi clocks line in B200_PROFILING.md, without spawning a process that takes the driver lock every 200 ms)."""
+    nvidia-smi clocks line in B200_PROFILING.md).  Every NVML query takes the driver lock and stalls kernel launches
+    (measured: 6 ms/step with a background thread sampling every 0.1 s, and occasional ~0.2 s stalls of a single step even
+    at 0.4 s), so there is no sampling thread: the main thread takes a sample every few steps inside the timed loop, right
+    after the step's loss read-back, when no launch is in flight (the SM clock is still the clock under load)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
-        self.period = float(os.environ.get("B200SCN_NVML_PERIOD", "0.4"))
-        self.t = threading.Thread(target=self._run, daemon=True)
+        self.index, self.rows = index, []
         self.h = None
         try:
             import pynvml
@@ -56,32 +56,28 @@ class ClockSampler:
             phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.sample()          # first-call costs (library initialisation) stay outside the timed region
+            self.rows.clear()
         except Exception:
             self.h = None
 
-    def _run(self):
-        nv = self.nv
-        while not self.stop:
-            try:
-                t0 = time.perf_counter()
-                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                self.rows.append((sm, rs, time.perf_counter() - t0))
-            except Exception:
-                pass
-            # every query holds the driver lock and stalls kernel launches (measured ~15 ms of step time per sample),
-            # so sample sparsely: two or three samples inside a 20-step timed region
-            time.sleep(self.period)
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            nv = self.nv
+            t0 = time.perf_counter()
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            self.rows.append((sm, rs, time.perf_counter() - t0))
+        except Exception:
+            pass
 
     def __enter__(self):
-        if self.h is not None:
-            self.t.start()
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        if self.h is not None:
-            self.t.join(timeout=2)
+        pass
 
     def summary(self):
         if self.h is None or not self.rows:
@@ -240,7 +236,7 @@ def run_b200(args):
                 ms["allocated_bytes.all.current"] / 1e9, ms["allocated_bytes.all.peak"] / 1e9))
         return loss
 
-    def timed(from_host, prof):
+    def timed(from_host, prof, sampler=None):
         for i in range(args.warmup):
             step(i, from_host)
         torch.cuda.synchronize()
@@ -263,6 +259,8 @@ def run_b200(args):
             # host runs a step ahead, two steps' activations are alive at once and the caching allocator occasionally
             # grows (cudaMalloc + implicit sync, ~0.1-0.2 s) inside the timed region
             loss_host = loss.item()  # noqa: F841
+            if sampler is not None and (i % 6 == 3 or (args.steps <= 3 and i == args.steps - 1)):
+                sampler.sample()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -284,8 +282,8 @@ def run_b200(args):
     # allocator priming (untimed, before any warm-up): site counts differ per batch, so torch's caching allocator needs to
     # have met every distinct batch before its block pool stops growing (cudaMalloc inside a step synchronises): whole
     # cycles over the distinct batches (at least four) until a cycle passes without a new cudaMalloc, at most 8 cycles.
-    # (expandable_segments was tried and made step times erratic: 46-106 ms.)  The NVML sampler
-    # thread starts here too: its first queries take the driver lock for ~0.2 s, which must not land in a timed step.
+    # (expandable_segments was tried and made step times erratic: 46-106 ms.)  (The NVML handle
+    # is opened here too: its first queries take the driver lock for ~0.2 s, which must not land in a timed step.)
     with ClockSampler(local) as clk:
         mallocs = -1
         for cycle in range(8):
@@ -297,8 +295,10 @@ def run_b200(args):
             if cycle >= 3 and now == mallocs:
                 break
             mallocs = now
-        clk.rows.clear()
-        ms, vox, launches, _ = timed(False, False)         # headline: device-resident inputs, nothing but the step
+        # one discarded rehearsal of the timed loop: whatever still grows on first use of this exact call sequence (caching
+        # allocator blocks: observed as a 0.1-0.25 s stall of one step in the first timed loop of ~1 run in 3) happens here
+        timed(False, False)
+        ms, vox, launches, _ = timed(False, False, clk)         # headline: device-resident inputs, nothing but the step
     clocks = clk.summary()
     ms_e, vox_e, _, _ = timed(True, False)                 # end to end: pinned host inputs, H2D inside, loss read back
     # roofline pass: the same K steps again with CUDA events around every conv / BN launch (kept out of the headline
