@@ -1,0 +1,152 @@
+"""The reference's OWN encoder file on the shim: tests/golden/reference_models_SparseConvNet.py.fixture is
+/root/reference/models/SparseConvNet.py byte for byte (made by tests/golden/make_reference_fixture.py).  It is executed
+here with `import sparseconvnet as scn` resolving to this repository's package (GPU tests) or to the CPU oracle, plus the
+stubs SURVEY.md Appendix A lists (`easydict`, `utils.registry`), and driven the way train.py drives it: the registry
+builds the class from the yaml `structure` keys (models/SparseConvNet.py:28-31) and `SparseConvBase_.forward` gets an
+EasyDict batch {coords, feature, batch_offsets} (models/SparseConvNet.py:34-55), coords on the CPU as int64
+(train.py:58 moves only the features).  Outputs and gradients of the two executions must agree."""
+import importlib
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+from _util import copy_params, rel_err
+
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_models_SparseConvNet.py.fixture")
+
+
+class _EasyDict(dict):
+    """Stand-in for easydict.EasyDict (absent from the image): attribute access over a dict."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class _Registry:
+    """Stand-in for utils/registry.py:1-95 (register(**kw) decorator + get)."""
+
+    def __init__(self):
+        self.map = {}
+
+    def register(self, obj=None, suffix=None, **kw):
+        def deco(c):
+            self.map[c.__name__] = (c, kw)
+            return c
+        return deco if obj is None else deco(obj)
+
+    def get(self, name):
+        return self.map[name]
+
+
+def load_reference_models(scn_module):
+    """Execute the reference file with `sparseconvnet` bound to `scn_module`; -> (module, registry, EasyDict)."""
+    saved = {k: sys.modules.get(k) for k in ("sparseconvnet", "easydict", "utils", "utils.registry")}
+    reg = _Registry()
+    ed = types.ModuleType("easydict")
+    ed.EasyDict = _EasyDict
+    ut = types.ModuleType("utils")
+    ur = types.ModuleType("utils.registry")
+    ur.MODEL_REGISTRY = reg
+    ut.registry = ur
+    sys.modules.update({"sparseconvnet": scn_module, "easydict": ed, "utils": ut, "utils.registry": ur})
+    try:
+        mod = types.ModuleType("reference_models_SparseConvNet")
+        src = open(FIXTURE).read()
+        exec(compile(src, FIXTURE, "exec"), mod.__dict__)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod, reg, _EasyDict
+
+
+# yaml `structure` blocks of the reference configs (config/3DUNet*_*.yaml: m, dimension, full_scale, block_reps,
+# residual_blocks [, downsample]), at reduced width/points so that the CPU oracle finishes in seconds
+CASES = [
+    ("SparseConvUNet", dict(m=16, dimension=3, full_scale=4096, block_reps=1, residual_blocks=False), 20),
+    ("SparseConvUNet", dict(m=32, dimension=3, full_scale=4096, block_reps=2, residual_blocks=True), 50),
+    ("SparseConvFCNet", dict(m=16, dimension=3, full_scale=4096, block_reps=1, residual_blocks=False), 20),
+    ("SparseConvFCNetNarrow", dict(m=16, dimension=3, full_scale=4096, block_reps=1, residual_blocks=True), 20),
+    ("SparseConvFCNetDirectUpPool", dict(m=16, dimension=3, full_scale=4096, block_reps=2, residual_blocks=True), 50),
+    ("SparseConvFCNetDirectUpPoolLight", dict(m=16, dimension=3, full_scale=4096, block_reps=2, residual_blocks=True,
+                                              downsample=[4, 4]), 50),
+]
+
+
+def _build(scn_module, name, kw):
+    _, reg, edict = load_reference_models(scn_module)
+    cls, meta = reg.get(name)
+    torch.manual_seed(0)
+    model = cls(name, **kw)                       # asserts name == class name (models/SparseConvNet.py:30)
+    return model, meta, edict
+
+
+def _oracle():
+    from oracle import scn_oracle
+    return scn_oracle
+
+
+def test_fixture_is_the_reference_file():
+    import hashlib
+    lines = open(FIXTURE, "rb").read().split(b"\n", 3)
+    assert b"sha256 of the original: " in lines[1]
+    want = lines[1].split(b"sha256 of the original: ")[1].strip().decode()
+    assert hashlib.sha256(lines[3]).hexdigest() == want
+    if os.path.exists("/root/reference/models/SparseConvNet.py"):
+        assert open("/root/reference/models/SparseConvNet.py", "rb").read() == lines[3]
+
+
+@pytest.mark.parametrize("name,kw,scale", CASES[:1] + CASES[4:5])
+def test_reference_models_run_on_the_oracle(name, kw, scale):
+    """CPU: the reference file executes on the oracle namespace (proves the loader + stubs; feeds the GPU comparison)."""
+    from b200scn_synth import make_batch
+    model, meta, edict = _build(_oracle(), name, kw)
+    coords, feats, offs = make_batch([0], scale, n_points=3000)
+    out = model(edict(coords=coords, feature=feats, batch_offsets=offs), istrain=True)
+    assert out.shape == (1, meta["embed_length"](kw["m"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,kw,scale", CASES)
+def test_reference_models_on_the_shim_match_the_oracle(name, kw, scale):
+    import sparseconvnet as scn
+    from b200scn_synth import make_batch
+    scn.set_precision("fp32")
+    model_r, meta, edict = _build(_oracle(), name, kw)
+    model_g, _, _ = _build(scn, name, kw)
+    copy_params(model_r, model_g)
+    model_g.cuda()                                                    # train.py:34
+    coords, feats, offs = make_batch([0, 1], scale, n_points=9000)
+    fr = feats.clone().requires_grad_(True)
+    fg = feats.clone().cuda().requires_grad_(True)                    # train.py:58: only the features move
+    for istrain in (False, True):
+        o_r = model_r(edict(coords=coords, feature=fr, batch_offsets=offs), istrain=istrain)
+        o_g = model_g(edict(coords=coords, feature=fg, batch_offsets=offs), istrain=istrain)
+        want = (2, meta["embed_length"](kw["m"])) if istrain else (coords.shape[0], meta["embed_length"](kw["m"]))
+        assert tuple(o_g.shape) == tuple(o_r.shape) == want
+        assert rel_err(o_g, o_r) < 1e-3
+    torch.manual_seed(1)
+    go = torch.randn_like(o_r)
+    o_r.backward(go)
+    o_g.backward(go.cuda())
+    assert rel_err(fg.grad, fr.grad) < 2e-3
+    worst = max(rel_err(pg.grad, pr.grad) for pg, pr in zip(model_g.parameters(), model_r.parameters()))
+    assert worst < 5e-3, worst     # real ReLU nets: borderline mask flips move gradients (tests/test_gpu_nets.py counts them)
+    # state_dict keys are the checkpoint contract (train.py:37,91)
+    assert list(model_g.state_dict().keys()) == list(model_r.state_dict().keys())
