@@ -14,8 +14,8 @@ class FlatGrads:
     asynchronously, so the transfer runs under the rest of the backward pass -- measured on 2 B200s of one box the
     un-overlapped 120 MB all-reduce cost 14 ms of a 58 ms step.  `allreduce_mean()` (after backward) reduces whatever is
     still pending, waits, scales and unpacks in place.
-    (Gradients are NOT kept as views of the flat buffer: autograd would then add into them, one extra kernel per
-    parameter and step.)"""
+    (During backward gradients are NOT views of the flat buffer -- autograd would then add into them, one extra kernel per
+    parameter and step; AFTER the all-reduce every .grad is re-pointed at its slice, so there is no unpack copy.)"""
 
     def __init__(self, params, bucket_bytes=16 << 20, group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -40,19 +40,29 @@ class FlatGrads:
                 self.bucket_of[i] = b
         self._pending = None       # per bucket: parameters still missing this step
         self._works = []
-        self._launched = []
+        self._ready, self._next, self._ev = [], 0, None
         self._hooks = []
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then one division
+        self.op = dist.ReduceOp.SUM
+        if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            self.op = dist.ReduceOp.AVG
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             for i, p in enumerate(self.params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
 
     # ------------------------------------------------------------------ per step
     def zero(self):
+        """Start of a step (before forward).  One backward per step: a second backward without zero() is refused."""
         for p in self.params:
             p.grad = None
+        self.zero_state_only()
+
+    def zero_state_only(self):
         self._pending = [hi - lo for lo, hi, _, _ in self.buckets]
         self._works = []
-        self._launched = [False] * len(self.buckets)
+        self._ready = [False] * len(self.buckets)
+        self._next = 0             # buckets are launched strictly in index order on every rank (matching collectives)
+        self._ev = None
 
     def _make_hook(self, i):
         def hook(_p):
@@ -60,40 +70,61 @@ class FlatGrads:
                 return
             b = self.bucket_of[i]
             self._pending[b] -= 1
+            if self._pending[b] < 0:
+                raise RuntimeError("FlatGrads: a parameter received a second gradient in one step; call zero() before "
+                                   "every backward (one backward per step is supported)")
             if self._pending[b] == 0:
-                self._launch(b)
+                self._ready[b] = True
+                self._launch_ready()
         return hook
+
+    def _launch_ready(self):
+        # a bucket only goes out once every bucket before it has gone out: a rank whose buckets fill in another order
+        # (data-dependent branches, parameters without a gradient) still issues the same collectives in the same order
+        while self._next < len(self.buckets) and self._ready[self._next]:
+            self._launch(self._next)
+            self._next += 1
 
     def _launch(self, b):
         lo, hi, f0, f1 = self.buckets[b]
         grads = [self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i])
                  for i in range(lo, hi)]
-        for i, g in zip(range(lo, hi), grads):
-            if self.params[i].grad is None:
-                self.params[i].grad = g
         torch._foreach_copy_(self.views[lo:hi], grads)
-        self._works.append(dist.all_reduce(self.flat[f0:f1], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        self._launched[b] = True
+        # AVG: the 1/world scale happens inside the collective (no separate pass over the flat buffer)
+        self._works.append(dist.all_reduce(self.flat[f0:f1], op=self.op, group=self.group, async_op=True))
 
     def allreduce_mean(self, group=None):
+        """After backward: send what is still pending (in order), wait, and point every .grad at its slice of the reduced
+        flat buffer (no unpack copy: the optimiser reads the flat buffer through the views).  Returns nothing; the time the
+        compute stream spent waiting for the collectives is available from `exposed_ms()` after a synchronize."""
         world = dist.get_world_size(self.group if group is None else group)
         if world <= 1:
             return
         if self._pending is None:          # zero() was not called this step: everything is still to do
             self.zero_state_only()
-        for b in range(len(self.buckets)):
-            if not self._launched[b]:      # parameters without a gradient this step, or hooks not registered
-                self._launch(b)
+        for b in range(self._next, len(self.buckets)):   # parameters without a gradient this step, or hooks not registered
+            self._launch(b)
+        self._next = len(self.buckets)
+        if self.flat.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for w in self._works:
             w.wait()
-        self.flat.div_(world)
-        torch._foreach_copy_([p.grad for p in self.params], self.views)
+        if self.flat.is_cuda:
+            e1.record()
+            self._ev = (e0, e1)
+        if self.op != dist.ReduceOp.AVG:
+            self.flat.div_(world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
         self._pending = None
 
-    def zero_state_only(self):
-        self._pending = [hi - lo for lo, hi, _, _ in self.buckets]
-        self._works = []
-        self._launched = [False] * len(self.buckets)
+    def exposed_ms(self):
+        """Milliseconds the compute stream waited for the step's collectives (CUDA events around the waits); call after
+        torch.cuda.synchronize().  Everything else of the all-reduce ran under backward."""
+        if self._ev is None:
+            return 0.0
+        return self._ev[0].elapsed_time(self._ev[1])
 
 
 def shard_scenes(n_scenes, rank, world):

@@ -39,10 +39,9 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
     if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, W))
       return set_error("gather_conv: TF32 path needs Cin %% 8 == 0, Cout %% 16 == 0, Cout <= 1024, 16-byte aligned rows "
                        "(got %d -> %d, lda %lld)", Cin, Cout, (long long)lda);
-    // B200SCN_TC_TMA=1 selects the TMA tile::gather4 producer variant.  Measured on B200 (profiles/r1_tma_gather4.txt):
+    // option tc_tma=1 selects the TMA tile::gather4 producer variant.  Measured on B200 (profiles/r1_tma_gather4_shapes.txt):
     // 128-byte gather4 boxes run at ~1 row / 15 cycles / SM, 2.2x slower than per-lane cp.async, so it is not the default.
-    const char *e = getenv("B200SCN_TC_TMA");
-    if (e && atoi(e) == 1 && Cout <= 256)
+    if (g_opt.tc_tma == 1 && Cout <= 256)
       return gather_conv_tma(A, lda, n_in, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
     return gather_conv_tc(A, lda, map, n_out, K, W, Cin, Cout, addend, ldadd, out, ldo, (cudaStream_t)stream);
   }
@@ -77,6 +76,20 @@ extern "C" int b200scn_gather_conv_tf32_ok(int Cin, int Cout, int64_t lda) {
   return (Cin % 8 == 0) && (Cout % 16 == 0) && Cout >= 16 && Cout <= 1024 && (lda % 4 == 0);
 }
 
+namespace b200scn { Options g_opt; }
+
+extern "C" int b200scn_set_option(const char *name, int value) {
+  if (!name) return set_error("set_option: NULL name");
+  if (!strcmp(name, "tc_tma")) g_opt.tc_tma = value;
+  else if (!strcmp(name, "tc_msub")) g_opt.tc_msub = value;
+  else if (!strcmp(name, "tc_nsplit")) g_opt.tc_nsplit = value;
+  else if (!strcmp(name, "dw_chunk")) g_opt.dw_chunk = value >= 512 ? value : 512;
+  else if (!strcmp(name, "halo_pf")) g_opt.halo_pf = value;
+  else if (!strcmp(name, "halo_one_cta")) g_opt.halo_one_cta = value;
+  else return set_error("set_option: unknown option '%s'", name);
+  return 0;
+}
+
 extern "C" int b200scn_set_device(int device) {
   SCN_CUDA(cudaSetDevice(device));
   return 0;
@@ -109,7 +122,37 @@ __global__ void prep_weight_kernel(const float *__restrict__ w0, int K, int a, i
     out[e] = __uint_as_float(t);
   }
 }
+// Both GEMM directions of one layer in ONE launch (forward operand: w0[k]; backward-input operand: w0[k]^T, offsets
+// mirrored when flip_bwd): out_fwd (K,b,a), out_bwd (K,a,b); each parameter element is read once and written twice.
+__global__ void prep_weight_both_kernel(const float *__restrict__ w0, int K, int a, int b, int flip_bwd,
+                                        float *__restrict__ out_fwd, float *__restrict__ out_bwd) {
+  const int64_t n = (int64_t)K * a * b;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e / ((int64_t)a * b));
+    const int r = (int)(e - (int64_t)k * a * b);
+    uint32_t t;
+    // backward operand: coalesced read and write of w0[kk] as stored
+    const int kk = flip_bwd ? K - 1 - k : k;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__ldg(w0 + (int64_t)kk * a * b + r)));
+    out_bwd[e] = __uint_as_float(t);
+    // forward operand: out_fwd[k][co][ci] = w0[k][ci][co] (strided read of a matrix that sits in L1/L2)
+    const int co = r / a, ci = r - co * a;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__ldg(w0 + ((int64_t)k * a + ci) * b + co)));
+    out_fwd[e] = __uint_as_float(t);
+  }
+}
 }  // namespace b200scn
+
+extern "C" int b200scn_prep_weight_tf32_both(const float *w0, int K, int a, int b, int flip_bwd, float *out_fwd,
+                                             float *out_bwd, void *stream) {
+  const int64_t n = (int64_t)K * a * b;
+  if (n <= 0) return 0;
+  const unsigned blocks = (unsigned)min((int64_t)kNumSMs * 8, ceil_div(n, 256));
+  prep_weight_both_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w0, K, a, b, flip_bwd, out_fwd, out_bwd);
+  SCN_CHECK_LAUNCH("prep_weight_tf32_both");
+  count_launch(1);
+  return 0;
+}
 
 extern "C" int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transposed, int flip, float *out,
                                         void *stream) {

@@ -27,6 +27,17 @@ void count_launch(int n);  // kernels enqueued by this library (b200scn_launch_c
       return b200scn::set_error("%s: %s", #call, cudaGetErrorString(e__));  \
   } while (0)
 
+// Tuning / test knobs, set through b200scn_set_option (never read from the environment on the launch path).
+struct Options {
+  int tc_tma = 0;        // 1: gather kernel with TMA tile::gather4 producers (measured 2.2x slower; kept for comparison)
+  int tc_msub = 0;       // 0 auto, 1 / 2: accumulators per CTA of the gather kernel
+  int tc_nsplit = 0;     // 0 auto, >0: split the offsets of the gather kernel over this many CTAs
+  int dw_chunk = 4096;   // pairs per CTA of the pair-list weight-gradient kernel
+  int halo_pf = -1;      // L2 prefetch distance of the tiled kernel in tiles (-1 auto, 0 off)
+  int halo_one_cta = 0;  // 1: force one CTA per SM in the tiled kernel
+};
+extern Options g_opt;
+
 constexpr int kNumSMs = 148;
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 

@@ -149,6 +149,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const
       "f"(c.z), "f"(c.w), "f"(d.x), "f"(d.y), "f"(d.z), "f"(d.w)
       : "memory");
 }
+// fp32 -> nearest TF32 (ties away), in place.  tcgen05.mma kind::tf32 TRUNCATES its operands to a 10-bit mantissa: a
+// one-sided error of up to 2^-10 whose mean (~3.5e-4 relative) does not average out over the reduction -- measured as a
+// coherent ~5e-4 per truncated operand in the per-op parity tests.  Rounding here makes the error zero-mean.
+__device__ __forceinline__ float rna1(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+__device__ __forceinline__ void rna4(float4 &v) { v.x = rna1(v.x); v.y = rna1(v.y); v.z = rna1(v.z); v.w = rna1(v.w); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by ONE thread
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -352,6 +361,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
             a3 = ldg_f4(src + 12);
           }
         }
+        rna4(a0); rna4(a1); rna4(a2); rna4(a3);
       };
       auto prefetch = [&](int v2_) {
         const int ki = 2 * (v2_ - kb * nk2);
@@ -527,12 +537,15 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
                        int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k,
                        int w_row0, cudaStream_t st) {
   auto kern = halo_conv_tc_kernel<NT, NS, MINB>;
-  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  static int smem_set = 0;   // per template instantiation: the attribute only ever needs to grow
+  if ((int)L.total > smem_set) {
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
   if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
-  int pf_dist = kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
-  if (const char *e = getenv("B200SCN_HALO_PF")) pf_dist = atoi(e);   // experiment hook (0 = off)
+  const int pf_dist = g_opt.halo_pf >= 0 ? g_opt.halo_pf : kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
   kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
                                                             (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,
                                                             acc_cols, pf_dist, w_rows_per_k, w_row0);
@@ -549,15 +562,21 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
   // to kHaloMaxW slots; with a large halo capacity the same kernel simply runs one CTA per SM.
   const int acc_cols = (Cout + 31) & ~31;
   const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
-  auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 4, <= kHaloMaxW
+  // The weight ring must hold every stage the A slots can have in flight (NS slots x 2 stages): a builder vouches for its
+  // visit's weight slices through a PARITY wait on wfull, and a parity wait on a ring slot that is a whole ring cycle behind
+  // succeeds on the previous cycle's completion -- the MMA then reads the previous stage's weights (found by
+  // tests/test_gpu_determinism.py at hcap = 512, where only 4 ring slots fitted beside 3 A slots: 1.3 % wrong output).
+  const int NS = acc_cols <= 64 ? 3 : 2;
+  const int nw_min = 2 * NS;
+  auto fit = [&](uint32_t budget, int &nw_out) {   // even, >= 2 NS, <= kHaloMaxW
     int nw = kHaloMaxW;
-    while (nw > 4 && halo_layout(nw, Cout, hcap).total > budget) nw -= 2;
+    while (nw > nw_min && halo_layout(nw, Cout, hcap).total > budget) nw -= 2;
     nw_out = nw;
     return halo_layout(nw, Cout, hcap).total <= budget;
   };
   int nw = 0;
   bool two = fit(half, nw);
-  if (const char *e = getenv("B200SCN_HALO_CTAS")) two = two && atoi(e) != 1;   // experiment hook
+  if (g_opt.halo_one_cta) two = false;   // test hook (b200scn_set_option)
   if (!two && !fit(whole, nw))
     return set_error("subm_conv_tiled: shared memory too small for Cout %d, hcap %d", Cout, hcap);
   const HaloSmem L = halo_layout(nw, Cout, hcap);
@@ -602,7 +621,11 @@ int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hc
   if (n >= ((int64_t)1 << 31)) return set_error("tile_plan: too many rows");
   if (reinterpret_cast<uintptr_t>(lmap) & 15) return set_error("tile_plan: lmap must be 16-byte aligned");
   const size_t smem = sizeof(int) * (kTileMap + kPlanHash) + sizeof(unsigned short) * kPlanHash;
-  SCN_CUDA(cudaFuncSetAttribute(tile_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool smem_set = false;
+  if (!smem_set) {
+    SCN_CUDA(cudaFuncSetAttribute(tile_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = true;
+  }
   tile_plan_kernel<<<(unsigned)ceil_div(n, kTile), kPlanThreads, smem, (cudaStream_t)stream>>>(
       nbr, perm, (int)n, hcap, lmap, halo_ids, halo_n, kmask);
   SCN_CHECK_LAUNCH("tile_plan");

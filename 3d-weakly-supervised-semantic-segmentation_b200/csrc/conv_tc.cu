@@ -321,7 +321,11 @@ static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const
                             const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k, int w_row0,
                             cudaStream_t st) {
   auto kern = gather_conv_tc_kernel<NT, MSUB, NPW>;
-  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  static bool smem_set = false;   // per template instantiation: opt in to the full 227 KB once, not on every launch
+  if (!smem_set) {
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = true;
+  }
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (K*Cout_total, Cin) K-major stack
   if (make_tmap(&tmW, Wkm, (int64_t)K * w_rows_per_k, Cin, Cin, Cout)) return 1;
@@ -354,7 +358,7 @@ static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, 
   // (eight producer warps then gather for one CTA per SM; the weight slice of every stage is fetched once per 256 rows;
   //  measured: a win from Cout = 96 up, while Cout <= 64 is faster as two 128-row CTAs per SM)
   int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && Cout > 64 && 2 * Cout <= 512) ? 2 : 1;
-  if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
+  if (g_opt.tc_msub) msub = (g_opt.tc_msub == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
   int nstages = kMaxStages;
   TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
   while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(msub, Cout, K, --nstages);
@@ -366,7 +370,7 @@ static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, 
     nsplit = (int)min((int64_t)K, (int64_t)kNumSMs / tiles);
     if (nsplit > 9) nsplit = 9;
   }
-  if (const char *e = getenv("B200SCN_TC_NSPLIT")) nsplit = max(1, min(K, atoi(e)));  // test hook
+  if (g_opt.tc_nsplit > 0) nsplit = max(1, min(K, g_opt.tc_nsplit));  // test hook
   if (nsplit > 1) {
     if (ldo == Cout) SCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_out * Cout, st));
     else SCN_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * Cout, (size_t)n_out, st));
@@ -584,8 +588,7 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
   int64_t want_chunks = ceil_div((int64_t)kNumSMs * 4, (int64_t)K);
   int64_t chunk = ceil_div(n_pairs_max, want_chunks > 0 ? want_chunks : 1);
   if (chunk < 512) chunk = 512;
-  int64_t chunk_max = 4096;   // small chunks keep the region the resident CTAs work on (27 offsets x ~11 chunks) inside L2
-  if (const char *e = getenv("B200SCN_DW_CHUNK")) chunk_max = atoi(e) >= 512 ? atoi(e) : 512;   // experiment hook
+  const int64_t chunk_max = g_opt.dw_chunk;   // small chunks keep the region the resident CTAs work on (27 offsets x ~11 chunks) inside L2
   if (chunk > chunk_max) chunk = chunk_max;
   if (ceil_div(n_pairs_max, chunk) > 65535) chunk = ceil_div(n_pairs_max, 65535);
   chunk = ceil_div(chunk, kDwPairs) * kDwPairs;
@@ -595,7 +598,11 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
 #define SCN_LAUNCH_DW(NT)                                                                                        \
   do {                                                                                                           \
     auto kern = pair_dw_tc_kernel<NT>;                                                                           \
-    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    static bool smem_set = false;                                                                                \
+    if (!smem_set) {                                                                                             \
+      SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));             \
+      smem_set = true;                                                                                           \
+    }                                                                                                            \
     kern<<<grid, 32 * (kDwWarps + 1), smem, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, \
                                                   (int)chunk, Ca, Cg, nstages, idesc, dW, dw_kstride);           \
   } while (0)
@@ -800,7 +807,11 @@ static int launch_gather_tma(dim3 grid, const TcSmemLayout &L, int nstages, cons
                              const CUtensorMap &tmW, const int32_t *map, int64_t n_out, int64_t n_in, int K, int Cin,
                              int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, cudaStream_t st) {
   auto kern = gather_conv_tma_kernel<NT, MSUB>;
-  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  static bool smem_set = false;   // per template instantiation: opt in to the full 227 KB once, not on every launch
+  if (!smem_set) {
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = true;
+  }
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   kern<<<grid, kTmaThreads, L.total, st>>>(tmA, tmW, map, (int)n_out, (int)n_in, K, Cin, Cout, addend, ldadd, out, ldo,
                                            nstages, idesc, L.map_off, L.klist_off, L.bar_off);
@@ -812,7 +823,7 @@ int gather_conv_tma(const float *A, int64_t lda, int64_t n_in, const int32_t *ma
                     cudaStream_t st) {
   if (n_out <= 0) return 0;
   int msub = (n_out >= (int64_t)256 * kNumSMs * 2 && 2 * Cout <= 512) ? 2 : 1;
-  if (const char *e = getenv("B200SCN_TC_MSUB")) msub = (atoi(e) == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
+  if (g_opt.tc_msub) msub = (g_opt.tc_msub == 2 && 2 * Cout <= 512) ? 2 : 1;  // test hook
   int nstages = kMaxStages;
   TcSmemLayout L = tc_layout(msub, Cout, K, nstages);
   while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(msub, Cout, K, --nstages);
@@ -823,7 +834,7 @@ int gather_conv_tma(const float *A, int64_t lda, int64_t n_in, const int32_t *ma
     nsplit = (int)min((int64_t)K, (int64_t)kNumSMs / tiles);
     if (nsplit > 9) nsplit = 9;
   }
-  if (const char *e = getenv("B200SCN_TC_NSPLIT")) nsplit = max(1, min(K, atoi(e)));  // test hook
+  if (g_opt.tc_nsplit > 0) nsplit = max(1, min(K, g_opt.tc_nsplit));  // test hook
   if (nsplit > 1) {
     if (ldo == Cout) SCN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)n_out * Cout, st));
     else SCN_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * Cout, (size_t)n_out, st));

@@ -7,14 +7,14 @@ import sys
 import types
 
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
-from ._lib import B200SCNError, launch_count
+from ._lib import B200SCNError, launch_count, set_option
 from .metadata import Metadata, set_pyramid_hint
 from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, ConcatTable, Convolution,
                       Deconvolution, Identity, InputLayer, JoinTable, NetworkInNetwork, OutputLayer, Sequential,
                       SparseConvNetTensor, SubmanifoldConvolution, UnPooling)
 from .networks import FullyConvolutionalNet, UNet
 from .modules import MaxPooling, SceneMeanPooling, SparseToDense, set_fusion  # noqa: F401
-from .ops import get_precision, set_precision
+from .ops import get_precision, set_precision, set_tiled
 from .utils import checkpoint_restore, checkpoint_save, is_power2
 
 forward_pass_hidden_states = 0

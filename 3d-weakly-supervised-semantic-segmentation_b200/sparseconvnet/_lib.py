@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200scn_last_error": (ctypes.c_char_p, []),
     "b200scn_version": (_i32, []),
     "b200scn_set_device": (_i32, [_i32]),
+    "b200scn_set_option": (_i32, [ctypes.c_char_p, _i32]),
     "b200scn_launch_count": (ctypes.c_ulonglong, []),
     "b200scn_hash_capacity": (_i64, [_i64]),
     "b200scn_grid_scratch_bytes": (_sz, [_i64]),
@@ -42,12 +43,14 @@ SIGNATURES = {
     "b200scn_tile_plan": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b200scn_subm_conv_tiled": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
     "b200scn_prep_weight_tf32": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b200scn_prep_weight_tf32_both": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200scn_scatter_conv": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200scn_unpool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
-    "b200scn_bn_forward": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _i64, _vp, _vp]),
-    "b200scn_bn_backward": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200scn_bn_forward": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _i64, _vp, _i32, _vp]),
+    "b200scn_bn_backward": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200scn_bn_scratch_doubles": (_sz, [_i32]),
     "b200scn_input_features": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200scn_input_features_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200scn_output_features": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
@@ -98,6 +101,21 @@ def stream_for(t):
         check(lib.b200scn_set_device(idx))
         _bound_device[0] = idx
     return torch.cuda.current_stream(idx).cuda_stream
+
+
+def set_option(name, value):
+    """Kernel tuning / test knob of the C library (include/b200scn.h: b200scn_set_option)."""
+    check(lib.b200scn_set_option(name.encode(), int(value)))
+
+
+# environment overrides are read ONCE, here, never on the launch path
+for _env, _opt in (("B200SCN_TC_TMA", "tc_tma"), ("B200SCN_TC_MSUB", "tc_msub"), ("B200SCN_TC_NSPLIT", "tc_nsplit"),
+                   ("B200SCN_DW_CHUNK", "dw_chunk"), ("B200SCN_HALO_PF", "halo_pf"), ("B200SCN_HALO_CTAS", None)):
+    if os.environ.get(_env):
+        if _opt is None:
+            set_option("halo_one_cta", 1 if os.environ[_env] == "1" else 0)
+        else:
+            set_option(_opt, int(os.environ[_env]))
 
 
 def launch_count():

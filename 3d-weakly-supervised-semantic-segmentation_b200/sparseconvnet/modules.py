@@ -94,6 +94,12 @@ def _fusable_residual(m, nxt):
     return type(last) is SubmanifoldConvolution and last.bias is None
 
 
+def _bn_feeds_conv(m, nxt):
+    """BatchNorm(Leaky)ReLU directly followed by a convolution: its output is consumed by tensor-core operand fetches only."""
+    return isinstance(m, BatchNormalization) and isinstance(nxt, (SubmanifoldConvolution, Convolution, Deconvolution,
+                                                                   NetworkInNetwork))
+
+
 class Sequential(torch.nn.Sequential):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
@@ -108,12 +114,15 @@ class Sequential(torch.nn.Sequential):
                 skip = m._modules["0"](input)
                 branch = list(m._modules["1"]._modules.values())
                 y = input
-                for mod in branch[:-1]:
-                    y = mod(y)
+                for j, mod in enumerate(branch[:-1]):
+                    y = mod(y, feeds_conv=True) if _bn_feeds_conv(mod, branch[j + 1]) else mod(y)
                 input = branch[-1](y, addend=skip.features)
                 i += 2
                 continue
-            input = m(input)
+            if i + 1 < len(mods) and _bn_feeds_conv(m, mods[i + 1]):
+                input = m(input, feeds_conv=True)
+            else:
+                input = m(input)
             i += 1
         return input
 
@@ -429,12 +438,14 @@ class BatchNormalization(Module):
                 state_dict[prefix + new] = state_dict.pop(prefix + old)
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
-    def forward(self, input):
+    def forward(self, input, feeds_conv=False):
+        """feeds_conv: set by Sequential when the next module is a convolution -- on the TF32 path the output is then
+        written rounded to the nearest TF32 (the tensor core would truncate it when it fetches the operand)."""
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
         out = SparseConvNetTensor(None, input.metadata, input.spatial_size)
         out.features = ops.BatchNormFn.apply(input.features, self.weight, self.bias, self.running_mean,
                                              self.running_var, self.eps, self.momentum, self.training,
-                                             self.leakiness)
+                                             self.leakiness, feeds_conv)
         return out
 
     def input_spatial_size(self, out_size):

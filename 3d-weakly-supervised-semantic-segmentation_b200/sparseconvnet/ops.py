@@ -100,8 +100,9 @@ class GemmWeight:
     the offsets mirrored (flip: k -> K-1-k).  The fp32 kernels read (K,Cin_g,Cout_g), the tcgen05 kernels read the
     K-major form (K,Cout_g,Cin_g); exactly one of the two is a free view of w0, the other is one small copy."""
 
-    def __init__(self, w0, transposed=False, flip=False):
+    def __init__(self, w0, transposed=False, flip=False, prepared=None):
         self.w0, self.transposed, self.flip = w0, transposed, flip
+        self.prepared = prepared   # K-major TF32 operand made earlier (prep_both: forward makes the backward's as well)
         self.cin, self.cout = (w0.shape[2], w0.shape[1]) if transposed else (w0.shape[1], w0.shape[2])
         self.K = w0.shape[0]
 
@@ -113,12 +114,30 @@ class GemmWeight:
         return (w.transpose(1, 2) if self.transposed else w).contiguous()
 
     def kmajor(self):     # (K,Cout_g,Cin_g), rounded to the nearest TF32, one launch
+        if self.prepared is not None:
+            return self.prepared
         w0 = self.w0.contiguous()
         K, a, b = w0.shape
         out = torch.empty((K, self.cout, self.cin), dtype=torch.float32, device=w0.device)
         check(lib.b200scn_prep_weight_tf32(ptr(w0), K, a, b, 1 if self.transposed else 0, 1 if self.flip else 0,
                                            ptr(out), _lib.stream_for(w0)))
         return out
+
+
+def prep_both(w, flip_bwd):
+    """K-major TF32 operands of BOTH directions of one layer in one launch: (forward: w[k], backward-input: w[k]^T with the
+    offsets mirrored if flip_bwd).  The forward pass makes them together and hands the second to its backward, so a
+    training step prepares each layer's weights once instead of twice.  None when the tensor-core path is off."""
+    if _precision[0] != 1:
+        return None, None
+    w = w.contiguous()
+    K, a, b = w.shape
+    if lib.b200scn_gather_conv_tf32_ok(a, b, a) != 1 or lib.b200scn_gather_conv_tf32_ok(b, a, b) != 1:
+        return None, None
+    fwd = torch.empty((K, b, a), dtype=torch.float32, device=w.device)
+    bwd = torch.empty((K, a, b), dtype=torch.float32, device=w.device)
+    check(lib.b200scn_prep_weight_tf32_both(ptr(w), K, a, b, 1 if flip_bwd else 0, ptr(fwd), ptr(bwd), _lib.stream_for(w)))
+    return fwd, bwd
 
 
 def _use_tf32(gw, lda, x):
@@ -128,15 +147,21 @@ def _use_tf32(gw, lda, x):
 # Spatially tiled submanifold convolution (conv_halo.cu): halo capacity per 128-row tile and the smallest level it is
 # used for (below that the step is bound by host launch overhead, not by the kernel); B200SCN_HALO=1 forces it on for every
 # size, =0 off.
-_halo = {"hcap": int(os.environ.get("B200SCN_HALO_CAP", "384")), "min_rows": 128 * 148}
+_halo = {"hcap": int(os.environ.get("B200SCN_HALO_CAP", "384")), "min_rows": 128 * 148,
+         "mode": os.environ.get("B200SCN_HALO", "")}   # the environment is read once, at import
 
 
 def set_halo_capacity(hcap):
     _halo["hcap"] = int(hcap)
 
 
+def set_tiled(mode):
+    """'auto' (default: levels with >= 148 tiles), 'on' / 'off' (tests and experiments)."""
+    _halo["mode"] = {"auto": "", "on": "1", "off": "0", "": "", "1": "1", "0": "0"}[mode]
+
+
 def _use_tiled(n):
-    mode = os.environ.get("B200SCN_HALO", "")
+    mode = _halo["mode"]
     if mode == "0":
         return False
     return mode == "1" or n >= _halo["min_rows"]
@@ -221,7 +246,8 @@ class SubmanifoldConvFn(torch.autograd.Function):
     def forward(ctx, x, w, level, addend=None):
         ctx.level = level
         ctx.save_for_backward(x, w)
-        return subm_conv(x, level, GemmWeight(w), addend=addend)
+        fwd, ctx.w_bwd = prep_both(w, True) if ctx.needs_input_grad[0] else (None, None)
+        return subm_conv(x, level, GemmWeight(w, prepared=fwd), addend=addend)
 
     @staticmethod
     def backward(ctx, g):
@@ -230,7 +256,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
-            dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True))
+            dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True, prepared=ctx.w_bwd))
         if ctx.needs_input_grad[1]:
             if _precision[0] == 1 and _use_tiled(level.n):
                 pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
@@ -247,7 +273,8 @@ class ConvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return gather_conv(x, down.child_map(), down.coarse.n, down.K, GemmWeight(w), rules=down.fine.n)
+        fwd, ctx.w_bwd = prep_both(w, False) if ctx.needs_input_grad[0] else (None, None)
+        return gather_conv(x, down.child_map(), down.coarse.n, down.K, GemmWeight(w, prepared=fwd), rules=down.fine.n)
 
     @staticmethod
     def backward(ctx, g):
@@ -255,7 +282,7 @@ class ConvolutionFn(torch.autograd.Function):
         down = ctx.down
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True), down)
+            dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True, prepared=ctx.w_bwd), down)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
             dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
@@ -270,7 +297,8 @@ class DeconvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w), down)
+        fwd, ctx.w_bwd = prep_both(w, False) if ctx.needs_input_grad[0] else (None, None)
+        return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w, prepared=fwd), down)
 
     @staticmethod
     def backward(ctx, g):
@@ -278,7 +306,8 @@ class DeconvolutionFn(torch.autograd.Function):
         down = ctx.down
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, GemmWeight(w, transposed=True), rules=down.fine.n)
+            dx = gather_conv(g, down.child_map(), down.coarse.n, down.K, GemmWeight(w, transposed=True, prepared=ctx.w_bwd),
+                             rules=down.fine.n)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
             dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n)
@@ -315,17 +344,31 @@ class NetworkInNetworkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        return gather_conv(x, None, x.shape[0], 1, GemmWeight(w.unsqueeze(0)))
+        fwd, ctx.w_bwd = prep_both(w.unsqueeze(0), False) if ctx.needs_input_grad[0] else (None, None)
+        return gather_conv(x, None, x.shape[0], 1, GemmWeight(w.unsqueeze(0), prepared=fwd))
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = gather_conv(g, None, g.shape[0], 1, GemmWeight(w.unsqueeze(0), transposed=True))
+            dx = gather_conv(g, None, g.shape[0], 1, GemmWeight(w.unsqueeze(0), transposed=True, prepared=ctx.w_bwd))
         if ctx.needs_input_grad[1]:
             dw = pair_dw(x, g, None, None, None, 1, x.shape[0])[0]
         return dx, dw
+
+
+_bn_scratch = {}
+
+
+def bn_scratch(device):
+    """The persistent, zero-initialised, self-cleaning statistics scratch of b200scn_bn_forward / _backward for the current
+    stream of `device` (one buffer per (device, stream): calls on one stream are ordered, so they can share it)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _bn_scratch.get(key)
+    if buf is None:
+        buf = _bn_scratch[key] = torch.zeros(lib.b200scn_bn_scratch_doubles(1 << 20), dtype=torch.float64, device=device)
+    return buf
 
 
 class BatchNormFn(torch.autograd.Function):
@@ -333,21 +376,22 @@ class BatchNormFn(torch.autograd.Function):
     BatchNormalization_updateOutput / _backward (eps 1e-4, momentum 0.9 on the old value, App. B.8)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32=False):
         x, ldx = _c(x)
         n, C = x.shape
         dev = x.device
         y = alloc_rows(n, C, dev)
         save_mean = torch.empty(C, dtype=torch.float32, device=dev)
         save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        scratch = bn_scratch(dev)
         tok = _p0("bn_fwd", "bn", 12.0 * n * C, 0, 0.0, 0.0)
         check(lib.b200scn_bn_forward(ptr(x), ldx, n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
                                      ptr(save_mean), ptr(save_invstd), eps, momentum, 1 if train else 0, leak,
-                                     ptr(y), C, ptr(scratch), _lib.stream_for(x)))
+                                     ptr(y), C, ptr(scratch), 1 if (round_tf32 and _precision[0] == 1) else 0,
+                                     _lib.stream_for(x)))
         _p1(tok)
         ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
-        ctx.leak = leak
+        ctx.leak, ctx.train = leak, bool(train)
         return y
 
     @staticmethod
@@ -360,13 +404,13 @@ class BatchNormFn(torch.autograd.Function):
         dx = alloc_rows(n, C, dev)
         dweight = torch.empty(C, dtype=torch.float32, device=dev)
         dbias = torch.empty(C, dtype=torch.float32, device=dev)
-        scratch = torch.empty(2 * C, dtype=torch.float64, device=dev)
+        scratch = bn_scratch(dev)
         tok = _p0("bn_bwd", "bn", 20.0 * n * C, 0, 0.0, 0.0)
         check(lib.b200scn_bn_backward(ptr(x), ldx, ptr(g), ldg, n, C, ptr(weight), ptr(bias), ptr(save_mean),
-                                      ptr(save_invstd), ctx.leak, ptr(dx), C, ptr(dweight), ptr(dbias),
-                                      ptr(scratch), _lib.stream_for(x)))
+                                      ptr(save_invstd), ctx.leak, 1 if ctx.train else 0, ptr(dx), C, ptr(dweight),
+                                      ptr(dbias), ptr(scratch), _lib.stream_for(x)))
         _p1(tok)
-        return dx, dweight, dbias, None, None, None, None, None, None
+        return dx, dweight, dbias, None, None, None, None, None, None, None
 
 
 class InputFeaturesFn(torch.autograd.Function):

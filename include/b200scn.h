@@ -29,6 +29,9 @@ const char *b200scn_last_error(void);
 int b200scn_version(void);
 /* bind the calling thread of this library's CUDA runtime to `device` (one process per GPU) */
 int b200scn_set_device(int device);
+/* tuning / test knobs (process-wide; never read from the environment on the launch path): "tc_tma", "tc_msub",
+ * "tc_nsplit", "dw_chunk", "halo_pf", "halo_one_cta" -- kernel variants the heuristics would not pick at test sizes */
+int b200scn_set_option(const char *name, int value);
 /* number of kernels this library has enqueued since load (bench.py's gpu_launches) */
 unsigned long long b200scn_launch_count(void);
 
@@ -116,6 +119,10 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
  * matrices transposed unless `transposed` (transposed = 0: multiply by w0[k], out (K,b,a); = 1: by w0[k]^T, out (K,a,b)),
  * values rounded to the nearest TF32 (the tensor core would truncate).  Input of every precision = 1 entry point. */
 int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transposed, int flip, float *out, void *stream);
+/* both directions of one layer in one launch: out_fwd (K,b,a) = operand of "multiply by w0[k]" (forward), out_bwd (K,a,b) =
+ * operand of "multiply by w0[k]^T" with the offsets mirrored if flip_bwd (backward-input; flip for submanifold 3^3) */
+int b200scn_prep_weight_tf32_both(const float *w0, int K, int a, int b, int flip_bwd, float *out_fwd, float *out_bwd,
+                                  void *stream);
 
 /* out[map[j*K+k],:] = A[j,:] . W[k] for every present (j,k)   (Deconvolution_updateOutput,
  * Convolution backward-input).  Rows of `out` not addressed by map are left untouched. */
@@ -138,18 +145,25 @@ int b200scn_unpool_bwd(const float *d_out, int64_t ldd, const int32_t *child, in
                        int C, float *d_in, int64_t ldi, void *stream);
 
 /* ------------------------------------------------------------------ BatchNormReLU (A8) */
-/* BatchNormalization_updateOutput: train!=0 => batch statistics over the n rows (biased var), running
- * stats updated as r = momentum*r + (1-momentum)*batch (unbiased var); else running stats.
- * y = leaky_relu((x-mean)*invstd*weight+bias, leak).  scratch: 2*C doubles. */
+/* scratch: b200scn_bn_scratch_doubles(C) doubles, ZERO on entry and left zero on exit (self-cleaning: the reduction
+ * kernel's last block finalises the statistics and clears the accumulators, so one persistent zero-initialised buffer per
+ * stream serves every call; two launches per direction, no memset). */
+size_t b200scn_bn_scratch_doubles(int C);
+/* BatchNormalization_updateOutput: train!=0 => batch statistics over the n rows (biased var, sums taken about a pivot row),
+ * running stats updated as r = momentum*r + (1-momentum)*batch (unbiased var); else running stats.
+ * y = leaky_relu((x-mean)*invstd*weight+bias, leak).  Any C (column slices of 1024 inside).
+ * round_tf32 != 0: y is written rounded to the nearest TF32 -- for outputs consumed ONLY by tcgen05 convolutions, whose
+ * kind::tf32 operand fetch would otherwise truncate (operand rounding fused into the producer). */
 int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const float *weight,
                        const float *bias, float *running_mean, float *running_var, float *save_mean,
                        float *save_invstd, float eps, float momentum, int train, float leak,
-                       float *y, int64_t ldy, double *scratch, void *stream);
-/* BatchNormalization_backward (batch-statistics formula; the ReLU mask is recomputed from x, which
- * equals the sign of the forward output bit for bit). scratch: 2*C doubles. */
+                       float *y, int64_t ldy, double *scratch, int round_tf32, void *stream);
+/* BatchNormalization_backward; the ReLU mask is recomputed from x, which equals the sign of the forward output bit for
+ * bit.  train != 0: batch-statistics formula; train == 0 (forward used the running statistics, which do not depend on x):
+ * d_in = g * invstd * weight, d_weight / d_bias from the same sums. */
 int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
                         const float *weight, const float *bias, const float *save_mean,
-                        const float *save_invstd, float leak, float *dx, int64_t lddx,
+                        const float *save_invstd, float leak, int train, float *dx, int64_t lddx,
                         float *d_weight, float *d_bias, double *scratch, void *stream);
 
 /* ------------------------------------------------------------------ I/O layers (A1, A9) */

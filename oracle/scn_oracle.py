@@ -247,7 +247,7 @@ class _BNFn(torch.autograd.Function):
         y = (x - mean) * invstd * weight + bias
         out = torch.where(y > 0, y, leak * y)
         ctx.save_for_backward(x, out, weight, mean, invstd)
-        ctx.leak = leak
+        ctx.leak, ctx.train = leak, bool(train)
         return out
 
     @staticmethod
@@ -259,7 +259,10 @@ class _BNFn(torch.autograd.Function):
         xc = x - mean
         dotp = (xc * g).sum(0)
         d_weight = dotp * invstd
-        d_in = (g - d_bias / n - xc * dotp * invstd * invstd / n) * invstd * weight
+        if ctx.train:
+            d_in = (g - d_bias / n - xc * dotp * invstd * invstd / n) * invstd * weight
+        else:   # eval: mean / invstd are the running statistics, constants with respect to x (upstream asserts train here)
+            d_in = g * invstd * weight
         return d_in, d_weight, d_bias, None, None, None, None, None, None
 
 

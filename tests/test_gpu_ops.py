@@ -6,7 +6,7 @@ from _util import copy_params, random_cloud, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-TOL_TF32 = 2e-3   # TF32 operands (10-bit mantissa), fp32 accumulate: the stated tensor-core tolerance
+TOL_TF32 = 1e-3   # the north-star tolerance (TF32 operands, 10-bit mantissa; fp32 accumulate); measured <= 7e-4 per op
 
 
 @pytest.fixture(params=["fp32", "tf32", "tf32-msub2", "tf32-split3", "tf32-tma", "tf32-halo", "tf32-halo1", "tf32-halo-ovf"])
@@ -18,24 +18,22 @@ def precision(request):
     name = request.param
     scn.set_precision("fp32" if name == "fp32" else "tf32")
     if name == "tf32-msub2":
-        os.environ["B200SCN_TC_MSUB"] = "2"
+        scn.set_option("tc_msub", 2)
     if name == "tf32-split3":
-        os.environ["B200SCN_TC_NSPLIT"] = "3"
+        scn.set_option("tc_nsplit", 3)
     if name == "tf32-tma":
-        os.environ["B200SCN_TC_TMA"] = "1"
+        scn.set_option("tc_tma", 1)
     # spatially tiled submanifold kernel (conv_halo.cu) forced on at test sizes: two CTAs or one per SM, and a halo
     # capacity so small that most neighbours take the beyond-capacity route through the global map
-    os.environ["B200SCN_HALO"] = "1" if name.startswith("tf32-halo") else "0"
+    scn.set_tiled("on" if name.startswith("tf32-halo") else "off")
     if name == "tf32-halo1":
-        os.environ["B200SCN_HALO_CTAS"] = "1"
+        scn.set_option("halo_one_cta", 1)
     if name == "tf32-halo-ovf":
         scn.ops.set_halo_capacity(64)
     yield "fp32" if name == "fp32" else "tf32"
-    os.environ.pop("B200SCN_TC_MSUB", None)
-    os.environ.pop("B200SCN_TC_NSPLIT", None)
-    os.environ.pop("B200SCN_TC_TMA", None)
-    os.environ.pop("B200SCN_HALO", None)
-    os.environ.pop("B200SCN_HALO_CTAS", None)
+    for opt in ("tc_msub", "tc_nsplit", "tc_tma", "halo_one_cta"):
+        scn.set_option(opt, 0)
+    scn.set_tiled("auto")
     scn.ops.set_halo_capacity(384)
     scn.set_precision("fp32")
 
@@ -106,6 +104,40 @@ def test_batchnorm(c, leak):
     # eval mode uses the running statistics
     mg.eval(), mr.eval()
     assert rel_err(mg(xg).features, mr(xr).features) < TOL
+    # backward through eval mode: the running statistics are constants (no batch-statistics terms)
+    scn, ref, xg, xr, fg, fr = _pair(coords, feats, c)
+    for p in list(mg.parameters()) + list(mr.parameters()):
+        p.grad = None
+    torch.manual_seed(3)
+    og, o_r = mg(xg).features, mr(xr).features
+    go = torch.randn_like(o_r)
+    og.backward(go.cuda())
+    o_r.backward(go)
+    assert rel_err(fg.grad, fr.grad) < TOL
+    assert rel_err(mg.weight.grad, mr.weight.grad) < TOL and rel_err(mg.bias.grad, mr.bias.grad) < TOL
+
+
+def test_batchnorm_wide_and_offset_mean():
+    """C > 1024 (column slices) and |mean| >> std (the pivoted sums must not cancel): against torch in fp64."""
+    import sparseconvnet as scn
+    from sparseconvnet import ops
+    torch.manual_seed(0)
+    for n, C, shift in ((3000, 1280, 0.0), (20000, 64, 1000.0), (777, 36, 300.0)):
+        x = torch.randn(n, C, device="cuda") * 0.5 + shift
+        w = torch.rand(C, device="cuda") + 0.5
+        b = torch.randn(C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        xg = x.clone().requires_grad_(True)
+        y = ops.BatchNormFn.apply(xg, w, b, rm, rv, 1e-4, 0.9, True, 0.0)
+        xd = x.double().requires_grad_(True)
+        mean, var = xd.mean(0), xd.var(0, unbiased=False)
+        yd = torch.relu((xd - mean) / torch.sqrt(var + 1e-4) * w.double() + b.double())
+        assert float((y.double() - yd).abs().max()) < 2e-3 * max(1.0, shift * 1e-3 + 1)
+        assert float((rv.double() - (0.9 + 0.1 * xd.var(0, unbiased=True))).abs().max() / rv.abs().max()) < 1e-4
+        go = torch.randn_like(y)
+        y.backward(go)
+        yd.backward(go.double())
+        assert float((xg.grad.double() - xd.grad).norm() / xd.grad.norm()) < (5e-3 if shift == 0 else 5e-2)
 
 
 @pytest.mark.parametrize("a,b", [(64, 32), (32, 64), (7, 5)])

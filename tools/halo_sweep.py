@@ -16,9 +16,9 @@ for cin in [int(v) for v in os.environ.get("SWEEP_CIN", "32,96,128,160,192,224,2
         f = torch.randn(level.n, cin, device='cuda')
         w = torch.randn(27, cin, cout, device='cuda') * 0.1
         gw = ops.GemmWeight(w)
-        os.environ["B200SCN_HALO"] = "0"
+        scn.set_tiled("off")
         ref = ops.subm_conv(f, level, gw)
-        os.environ["B200SCN_HALO"] = "1"
+        scn.set_tiled("on")
         errs = []
         for rep in range(3):
             out = ops.subm_conv(f, level, gw)
