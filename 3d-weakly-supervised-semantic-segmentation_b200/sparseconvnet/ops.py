@@ -238,6 +238,35 @@ def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max, rules=None):
     return dw
 
 
+_dw_tiled = [True]
+
+
+def set_tiled_dw(on):
+    """Tile-stationary weight gradient (dw_tile.cu) on levels where the tiled forward kernel runs (default on)."""
+    _dw_tiled[0] = bool(on)
+
+
+def subm_dw_tiled(a, g, level):
+    """dW (27,Ca,Cg) of a submanifold convolution over the level's tile plan, or None if the shape is not taken."""
+    a, lda = _c(a)
+    g, ldg = _c(g)
+    Ca, Cg = a.shape[1], g.shape[1]
+    hcap = _halo["hcap"]
+    nbytes = lib.b200scn_subm_dw_tiled_scratch_bytes(level.n, hcap, Ca, Cg)
+    if nbytes == 0 or a.data_ptr() % 16 or g.data_ptr() % 16 or lda % 4 or ldg % 4:
+        return None
+    plan = level.tile_plan(hcap)
+    dw = torch.empty((27, Ca, Cg), dtype=torch.float32, device=a.device)
+    scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=a.device)
+    tok = _p0("tile_dw27", "subm_dw_tiled", 4.0 * (a.shape[0] * Ca + g.shape[0] * Cg) + 4.0 * 27 * Ca * Cg, level, 8.0,
+              2.0 * Ca * Cg)
+    check(lib.b200scn_subm_dw_tiled(ptr(a), lda, ptr(g), ldg, ptr(level.nbr), ptr(plan.perm), ptr(plan.lmap),
+                                    ptr(plan.halo_ids), ptr(plan.halo_n), hcap, level.n, Ca, Cg, ptr(dw), ptr(scratch),
+                                    nbytes, _lib.stream_for(a)))
+    _p1(tok)
+    return dw
+
+
 class SubmanifoldConvFn(torch.autograd.Function):
     """scn.SubmanifoldConvolution (models/SparseConvNet.py:62,117,119): replaces upstream
     SubmanifoldConvolution_updateOutput / _backward."""
@@ -258,11 +287,15 @@ class SubmanifoldConvFn(torch.autograd.Function):
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
             dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True, prepared=ctx.w_bwd))
         if ctx.needs_input_grad[1]:
-            if _precision[0] == 1 and _use_tiled(level.n):
-                pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
-            else:
-                pin, pout, offs = level.subm_pairs()
-            dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
+            tiled = _precision[0] == 1 and _use_tiled(level.n)
+            if tiled and _dw_tiled[0]:
+                dw = subm_dw_tiled(x, g, level)
+            if dw is None:
+                if tiled:
+                    pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
+                else:
+                    pin, pout, offs = level.subm_pairs()
+                dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
         return dx, dw, None, (g if ctx.needs_input_grad[3] else None)
 
 

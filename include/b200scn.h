@@ -115,6 +115,17 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
                             const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
                             const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream);
 
+/* Tile-stationary weight gradient of the submanifold convolution (weight-gradient half of
+ * SubmanifoldConvolution_backward) on the SAME plan as b200scn_subm_conv_tiled: dW (27,Ca,Cg) = sum over the rules of
+ * A[in]^T (x) G[out].  Each tile's G rows and distinct A rows are staged in shared memory once; accumulators for all offsets
+ * stay in tensor memory; per-CTA partials go to `scratch` and are summed in a fixed order (bit-reproducible, no atomics).
+ * scratch_bytes() returns 0 for shapes it does not take (use b200scn_pair_dw then). */
+size_t b200scn_subm_dw_tiled_scratch_bytes(int64_t n, int hcap, int Ca, int Cg);
+int b200scn_subm_dw_tiled(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *nbr,
+                          const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
+                          int hcap, int64_t n, int Ca, int Cg, float *dW, float *scratch, size_t scratch_bytes,
+                          void *stream);
+
 /* K-major TF32 operand of one GEMM direction from the parameter stack w0 (K,a,b) in one launch: offsets mirrored if flip,
  * matrices transposed unless `transposed` (transposed = 0: multiply by w0[k], out (K,b,a); = 1: by w0[k]^T, out (K,a,b)),
  * values rounded to the nearest TF32 (the tensor core would truncate).  Input of every precision = 1 entry point. */
