@@ -96,3 +96,6 @@ CONFIGS = {
     "cfg3_unet_m32_r2_res_s50_b5": ("SparseConvUNet", 32, 2, True, 50, 5),
     "cfg5_fcnet_m16_r2_res_s100_b6": ("SparseConvFCNet", 16, 2, True, 100, 6),
 }
+
+# eval-mode workloads: number of forward passes per step (val_reps; BASELINE.json configs[4] says 3)
+EVAL_REPS = {"cfg5_fcnet_m16_r2_res_s100_b6": 3}

@@ -18,6 +18,10 @@ int gather_conv_tc(const float *A, int64_t lda, const int32_t *map, int64_t n_ou
 int gather_conv_tma(const float *A, int64_t lda, int64_t n_in, const int32_t *map, int64_t n_out, int K,
                     const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo,
                     cudaStream_t st);
+int group_tiles(const int32_t *offsets_dev, int K, int64_t max_tiles, int32_t *tab, cudaStream_t st);
+int grouped_conv_tc(const float *A, int64_t lda, const int32_t *in_rows, const int32_t *out_rows, const int32_t *tab,
+                    int64_t max_tiles, int64_t n_out, int K, const float *Wkm, int Cin, int Cout, float *out, int64_t ldo,
+                    cudaStream_t st);
 bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg);
 int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a, const int32_t *pair_g,
                const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg, float *dW, cudaStream_t st);
@@ -57,6 +61,21 @@ int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_
   if (Cin < 1 || Cout < 1) return set_error("scatter_conv: bad channel counts %d -> %d", Cin, Cout);
   (void)precision;
   return scatter_conv_simt(A, lda, map, n_in, K, W, Cin, Cout, out, ldo, (cudaStream_t)stream);
+}
+
+int b200scn_group_tiles(const int32_t *offsets_dev, int K, int64_t max_tiles, int32_t *tab, void *stream) {
+  return group_tiles(offsets_dev, K, max_tiles, tab, (cudaStream_t)stream);
+}
+
+int b200scn_grouped_conv(const float *A, int64_t lda, const int32_t *in_rows, const int32_t *out_rows,
+                         const int32_t *tab, int64_t max_tiles, int64_t n_out, int K, const float *Wkm, int Cin,
+                         int Cout, float *out, int64_t ldo, void *stream) {
+  if (K < 1 || K > 64) return set_error("grouped_conv: K=%d outside [1,64]", K);
+  if (!gather_conv_tc_supported(A, lda, K, Cin, Cout, Wkm))
+    return set_error("grouped_conv: needs Cin %% 8 == 0, Cout %% 16 == 0, 16-byte aligned rows (got %d -> %d)", Cin, Cout);
+  if (reinterpret_cast<uintptr_t>(tab) & 15) return set_error("grouped_conv: tile table must be 16-byte aligned");
+  return grouped_conv_tc(A, lda, in_rows, out_rows, tab, max_tiles, n_out, K, Wkm, Cin, Cout, out, ldo,
+                         (cudaStream_t)stream);
 }
 
 int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,

@@ -200,7 +200,8 @@ bn_bwd_apply_kernel(const float *__restrict__ x, int64_t ldx, const float *__res
                     int64_t n, int C, int tpr, int rps, int64_t rows_per_block, const float *__restrict__ mean,
                     const float *__restrict__ invstd, const float *__restrict__ weight,
                     const float *__restrict__ bias, float leak, const float *__restrict__ d_weight,
-                    const float *__restrict__ d_bias, int train, float *__restrict__ dx, int64_t lddx) {
+                    const float *__restrict__ d_bias, int train, const float *__restrict__ addend, int64_t ldadd,
+                    float *__restrict__ dx, int64_t lddx) {
   const int tid = threadIdx.x;
   const int rg = tid / tpr, c0 = (tid - rg * tpr) * VEC;
   if (rg >= rps || c0 >= C) return;
@@ -235,6 +236,14 @@ bn_bwd_apply_kernel(const float *__restrict__ x, int64_t ldx, const float *__res
       const float yv = bn_affine(xv[v], m[v], is[v], w[v], b[v]);
       const float g = yv > 0.f ? gv[v] : leak * gv[v];
       ov[v] = (g - k0[v] - (xv[v] - m[v]) * k1[v]) * sc[v];
+    }
+    if (addend) {   // gradient arriving at x through another consumer (the residual skip): summed here, not by a separate pass
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(addend + r * ldadd + c0));
+        ov[0] += t.x; ov[1] += t.y; ov[2] += t.z; ov[3] += t.w;
+      } else {
+        ov[0] += __ldg(addend + r * ldadd + c0);
+      }
     }
     if (VEC == 4) *reinterpret_cast<float4 *>(dx + r * lddx + c0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
     else dx[r * lddx + c0] = ov[0];
@@ -297,8 +306,8 @@ static int bn_forward_slice(const float *x, int64_t ldx, int64_t n, int C, const
 
 static int bn_backward_slice(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
                              const float *weight, const float *bias, const float *save_mean, const float *save_invstd,
-                             float leak, int train, float *dx, int64_t lddx, float *d_weight, float *d_bias,
-                             double *scratch, bool vec, cudaStream_t st) {
+                             float leak, int train, const float *addend, int64_t ldadd, float *dx, int64_t lddx,
+                             float *d_weight, float *d_bias, double *scratch, bool vec, cudaStream_t st) {
   BnFinal fin = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, d_weight, d_bias};
   if (launch_reduce<1>(x, ldx, dy, lddy, n, C, save_mean, save_invstd, weight, bias, leak, scratch, fin, vec, st)) return 1;
   BnCfg cfg = bn_cfg(C, vec ? 4 : 1);
@@ -306,8 +315,8 @@ static int bn_backward_slice(const float *x, int64_t ldx, const float *dy, int64
   int64_t rows_per_block = ceil_div(n, blocks);
   if (rows_per_block < cfg.rps) rows_per_block = cfg.rps;
   blocks = ceil_div(n, rows_per_block);
-  if (vec) bn_bwd_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, d_weight, d_bias, train, dx, lddx);
-  else bn_bwd_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, d_weight, d_bias, train, dx, lddx);
+  if (vec) bn_bwd_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, d_weight, d_bias, train, addend, ldadd, dx, lddx);
+  else bn_bwd_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, dy, lddy, n, C, cfg.tpr, cfg.rps, rows_per_block, save_mean, save_invstd, weight, bias, leak, d_weight, d_bias, train, addend, ldadd, dx, lddx);
   SCN_CHECK_LAUNCH("bn_backward");
   count_launch(1);
   return 0;
@@ -342,8 +351,8 @@ int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const floa
 
 int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
                         const float *weight, const float *bias, const float *save_mean,
-                        const float *save_invstd, float leak, int train, float *dx, int64_t lddx, float *d_weight,
-                        float *d_bias, double *scratch, void *stream) {
+                        const float *save_invstd, float leak, int train, const float *addend, int64_t ldadd,
+                        float *dx, int64_t lddx, float *d_weight, float *d_bias, double *scratch, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 0) return set_error("batchnorm: C must be positive");
   if (n <= 0) {
@@ -351,12 +360,13 @@ int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t ld
     SCN_CUDA(cudaMemsetAsync(d_bias, 0, sizeof(float) * C, st));
     return 0;
   }
-  const bool vec = vec_ok(C, ldx, x) && vec_ok(C, lddy, dy) && vec_ok(C, lddx, dx);
+  const bool vec = vec_ok(C, ldx, x) && vec_ok(C, lddy, dy) && vec_ok(C, lddx, dx) && (!addend || vec_ok(C, ldadd, addend));
   const int width = vec ? 1024 : 256;
   for (int c0 = 0; c0 < C; c0 += width) {
     const int cs = C - c0 < width ? C - c0 : width;
     if (bn_backward_slice(x + c0, ldx, dy + c0, lddy, n, cs, weight + c0, bias + c0, save_mean + c0, save_invstd + c0, leak,
-                          train, dx + c0, lddx, d_weight + c0, d_bias + c0, scratch, vec, st))
+                          train, addend ? addend + c0 : nullptr, ldadd, dx + c0, lddx, d_weight + c0, d_bias + c0, scratch, vec,
+                          st))
       return 1;
   }
   return 0;

@@ -43,7 +43,20 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor map: rows x cols (cols contiguous, row pitch ld floats), box = box_rows x 32 floats, 128-byte swizzle
+// cuTensorMapEncodeTiled costs a few microseconds of host time per call and the weight operands of a step are prepared
+// into buffers the caching allocator hands back at the same addresses step after step: remember the last encodings
+// (a tensor map describes address + shape only, never contents, so a hit is always valid).
+struct TmapKey { const float *base; int64_t rows, ld; int cols, box_rows; };
+static thread_local struct { TmapKey key; CUtensorMap map; bool used; } g_tmap_cache[256];
+
 static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, int64_t ld, int box_rows) {
+  const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull + (uint64_t)rows * 31 + (uint64_t)box_rows;
+  auto &slot = g_tmap_cache[(h >> 32) & 255];
+  if (slot.used && slot.key.base == base && slot.key.rows == rows && slot.key.ld == ld && slot.key.cols == cols &&
+      slot.key.box_rows == box_rows) {
+    *m = slot.map;
+    return 0;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error("cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -55,6 +68,9 @@ static int make_tmap(CUtensorMap *m, const float *base, int64_t rows, int cols, 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %d ld %lld box %d", (int)r,
                                           (long long)rows, cols, (long long)ld, box_rows);
+  slot.key = TmapKey{base, rows, ld, cols, box_rows};
+  slot.map = *m;
+  slot.used = true;
   return 0;
 }
 
@@ -90,9 +106,23 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
                       const int32_t *__restrict__ map, int n_rows, int K, int Cin, int Cout,
                       const float *__restrict__ addend,
                       int64_t ldadd, float *__restrict__ out, int64_t ldo, int nstages, uint32_t idesc,
-                      uint32_t map_off, uint32_t klist_off, uint32_t bar_off, int w_rows_per_k, int w_row0) {
+                      uint32_t map_off, uint32_t klist_off, uint32_t bar_off, int w_rows_per_k, int w_row0,
+                      const int32_t *__restrict__ grp_in, const int32_t *__restrict__ grp_out,
+                      const int4 *__restrict__ grp_tab) {
   constexpr int ROWS = MSUB * 128;
   constexpr int NTHREADS = 32 * (NPW + 2);   // producers, MMA-issuing warp, weight-TMA warp
+  // GROUPED mode (strided Deconvolution forward / Convolution backward-input on the fine side, where every output row
+  // has exactly ONE rule): the rules arrive sorted by offset (the scn-form rulebook), a tile is a run of <= 128 rules of
+  // ONE offset -- grp_tab[tile] = {offset, first rule, count} -- so the tile is a single dense K-slice: input row
+  // grp_in[rule], output row grp_out[rule].  (The one-hot map this replaces wasted 7/8 of every staged A tile.)
+  const bool grouped = grp_tab != nullptr;
+  const int KM = grouped ? 1 : K;             // columns of the shared-memory map slice
+  int g_k = 0, g_start = 0, g_cnt = ROWS;
+  if (grouped) {
+    const int4 t = __ldg(grp_tab + blockIdx.x);
+    g_k = t.x; g_start = t.y; g_cnt = t.z;
+    if (g_cnt <= 0) return;                   // table slack beyond the live tiles (uniform for the CTA)
+  }
   constexpr int WPS = NPW / 4;  // producer warps per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -116,7 +146,9 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
   // The tile's slice of the map is one contiguous run of ROWS*K ints.  Full tiles copy it with 16-byte cp.async, all
   // in flight at once (a dependent load->store loop with a division per element cost ~15 % of the tile, measured with a
   // clock64 timeline of one CTA); the ragged last tile takes the scalar path.
-  {
+  if (grouped) {
+    for (int e = tid; e < ROWS; e += NTHREADS) smap[e] = e < g_cnt ? __ldg(grp_in + g_start + e) : -1;
+  } else {
     const int live = min(ROWS, n_rows - row0) * K;   // entries that belong to real rows
     const int32_t *msrc = map ? map + (int64_t)row0 * K : nullptr;
     if (msrc && live == ROWS * K && ((ROWS * K) & 3) == 0 && (reinterpret_cast<uintptr_t>(msrc) & 15) == 0) {
@@ -129,17 +161,21 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
   }
   __syncthreads();
   // offset k is present in this tile if any of its ROWS entries is: one warp-strided pass per offset
-  for (int k = warp; k < K; k += NTHREADS / 32) {
-    int any = 0;
-    for (int r = lane; r < ROWS; r += 32) any |= (smap[r * K + k] >= 0);
-    any = __any_sync(0xffffffffu, any);
-    if (lane == 0) kflag[k] = any;
+  if (!grouped) {
+    for (int k = warp; k < K; k += NTHREADS / 32) {
+      int any = 0;
+      for (int r = lane; r < ROWS; r += 32) any |= (smap[r * K + k] >= 0);
+      any = __any_sync(0xffffffffu, any);
+      if (lane == 0) kflag[k] = any;
+    }
   }
   __syncthreads();
   if (tid == 0) {
     int n = 0;
-    for (int k = 0; k < K; ++k)
-      if (kflag[k]) klist[n++] = k;
+    if (grouped) klist[n++] = g_k;
+    else
+      for (int k = 0; k < K; ++k)
+        if (kflag[k]) klist[n++] = k;
     // this CTA's share of the present offsets
     const int per = (n + nsplit - 1) / nsplit;
     const int lo = min(n, split * per), hi = min(n, lo + per);
@@ -185,7 +221,7 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
       for (int i = 0; i < NI; ++i) {
         const int r = rbase + rl + 4 * i;
         soff[i] = sw128(r, c);
-        mrow[i] = smap + r * K;
+        mrow[i] = smap + r * KM;
       }
       const int64_t lda4 = lda;
       for (int it = my_stage; it < T; it += nstages) {
@@ -199,7 +235,7 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
           const float *acol = A + chan;
           int idx[NI];
 #pragma unroll
-          for (int i = 0; i < NI; ++i) idx[i] = mrow[i][k];   // all map reads first, then the copies
+          for (int i = 0; i < NI; ++i) idx[i] = mrow[i][grouped ? 0 : k];   // all map reads first, then the copies
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
             const bool valid = idx[i] >= 0;
@@ -272,7 +308,11 @@ gather_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__re
     const bool vec = (ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     const int q = warp & 3;
     for (int m = warp >> 2; m < MSUB; m += NPW / 4) {
-      const int row = row0 + m * 128 + q * 32 + lane;
+      int row = row0 + m * 128 + q * 32 + lane;
+      if (grouped) {
+        const int pos = m * 128 + q * 32 + lane;
+        row = pos < g_cnt ? __ldg(grp_out + g_start + pos) : n_rows;   // n_rows = "no row"
+      }
       for (int c0 = 0; c0 < Cout; c0 += 16) {
         float v[16];
         if (T > 0) {
@@ -319,7 +359,8 @@ template <uint32_t NT, int MSUB, int NPW>
 static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const float *A, int64_t lda,
                             const int32_t *map, int64_t n_out, int K, const float *Wkm, int Cin, int Cout,
                             const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k, int w_row0,
-                            cudaStream_t st) {
+                            cudaStream_t st, const int32_t *grp_in = nullptr, const int32_t *grp_out = nullptr,
+                            const int4 *grp_tab = nullptr) {
   auto kern = gather_conv_tc_kernel<NT, MSUB, NPW>;
   static bool smem_set = false;   // per template instantiation: opt in to the full 227 KB once, not on every launch
   if (!smem_set) {
@@ -330,7 +371,69 @@ static int launch_gather_tc(dim3 grid, const TcSmemLayout &L, int nstages, const
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (K*Cout_total, Cin) K-major stack
   if (make_tmap(&tmW, Wkm, (int64_t)K * w_rows_per_k, Cin, Cin, Cout)) return 1;
   kern<<<grid, 32 * (NPW + 2), L.total, st>>>(tmW, A, lda, map, (int)n_out, K, Cin, Cout, addend, ldadd, out, ldo,
-                                              nstages, idesc, L.map_off, L.klist_off, L.bar_off, w_rows_per_k, w_row0);
+                                              nstages, idesc, L.map_off, L.klist_off, L.bar_off, w_rows_per_k, w_row0,
+                                              grp_in, grp_out, grp_tab);
+  return 0;
+}
+
+// tile table of the grouped mode: one entry {offset, first rule, rules} per run of <= 128 rules of one offset, in offset
+// order; entries beyond the live tiles get count 0.  offsets[K+1] is the rulebook's per-offset prefix (device memory).
+__global__ void group_tiles_kernel(const int32_t *__restrict__ offsets, int K, int max_tiles, int4 *__restrict__ tab) {
+  __shared__ int tbase[65];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < K; ++k) {
+      tbase[k] = acc;
+      acc += (offsets[k + 1] - offsets[k] + 127) >> 7;
+    }
+    tbase[K] = acc;
+  }
+  __syncthreads();
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < max_tiles; t += gridDim.x * blockDim.x) {
+    int4 e = make_int4(0, 0, 0, 0);
+    if (t < tbase[K]) {
+      int k = 0;
+      while (t >= tbase[k + 1]) ++k;
+      const int beg = offsets[k], cnt = offsets[k + 1] - beg, first = (t - tbase[k]) << 7;
+      e = make_int4(k, beg + first, min(128, cnt - first), 0);
+    }
+    tab[t] = e;
+  }
+}
+
+int group_tiles(const int32_t *offsets_dev, int K, int64_t max_tiles, int32_t *tab, cudaStream_t st) {
+  if (K < 1 || K > 64) return set_error("group_tiles: K=%d outside [1,64]", K);
+  if (max_tiles <= 0) return 0;
+  group_tiles_kernel<<<(unsigned)ceil_div(max_tiles, 256), 256, 0, st>>>(offsets_dev, K, (int)max_tiles,
+                                                                         reinterpret_cast<int4 *>(tab));
+  SCN_CHECK_LAUNCH("group_tiles");
+  count_launch(1);
+  return 0;
+}
+
+// out[out_rows[p]] = A[in_rows[p]] . W[offset of p] over an offset-sorted rule list (every output row named once)
+int grouped_conv_tc(const float *A, int64_t lda, const int32_t *in_rows, const int32_t *out_rows, const int32_t *tab,
+                    int64_t max_tiles, int64_t n_out, int K, const float *Wkm, int Cin, int Cout, float *out, int64_t ldo,
+                    cudaStream_t st) {
+  if (max_tiles <= 0) return 0;
+  for (int n0 = 0; n0 < Cout; n0 += 256) {
+    const int nc = Cout - n0 < 256 ? Cout - n0 : 256;
+    int nstages = kMaxStages;
+    TcSmemLayout L = tc_layout(1, nc, 1, nstages);
+    while (nstages > 2 && L.total > 227 * 1024) L = tc_layout(1, nc, 1, --nstages);
+    if (L.total > 227 * 1024) return set_error("grouped_conv_tc: shared memory %u too large", L.total);
+    dim3 grid((unsigned)max_tiles, 1);
+    int rc;
+#define SCN_ARGS grid, L, nstages, A, lda, nullptr, n_out, K, Wkm, Cin, nc, nullptr, 0, out + n0, ldo, Cout, n0, st, in_rows, out_rows, reinterpret_cast<const int4 *>(tab)
+    if (nc <= 32) rc = launch_gather_tc<32, 1, 16>(SCN_ARGS);
+    else if (nc <= 64) rc = launch_gather_tc<64, 1, 16>(SCN_ARGS);
+    else if (nc <= 128) rc = launch_gather_tc<128, 1, 16>(SCN_ARGS);
+    else rc = launch_gather_tc<256, 1, 16>(SCN_ARGS);
+#undef SCN_ARGS
+    if (rc) return rc;
+    SCN_CHECK_LAUNCH("grouped_conv_tc");
+    count_launch(1);
+  }
   return 0;
 }
 

@@ -45,6 +45,7 @@ static DwLayout dw_layout(int hcap, int Cg, int nbuf, int nst) {
   uint32_t o = 0;
   for (int b = 0; b < 2; ++b) {
     const bool live = b < nbuf;
+    if (live) o = (o + 1023) & ~1023u;            // the swizzled operand image needs a 1024-byte aligned base
     L.g_off[b] = live ? o : L.g_off[0];
     if (live) o += gb * kBlkG;                    // 1024-byte aligned blocks
     L.halo_off[b] = live ? o : L.halo_off[0];
@@ -66,7 +67,9 @@ static DwLayout dw_layout(int hcap, int Cg, int nbuf, int nst) {
 
 __device__ __forceinline__ float4 dt_lds_f4(uint32_t saddr) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  // not volatile (independent loads of a batch may be scheduled together) but a memory reader: never hoisted or merged
+  // across the barrier waits and stores around it
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
   return v;
 }
 __device__ __forceinline__ float dt_rna(float v) {
@@ -145,33 +148,50 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
       uint8_t *cm = reinterpret_cast<uint8_t *>(hids + hcap);
       const uint16_t *slmap = reinterpret_cast<const uint16_t *>(sm + L.lmap_off[b]);
       const int hn = __ldg(halo_n + tile);
-      // phase 1: the tile's plan slice
+      // phase 1: the tile's plan slice (asynchronous copies) and the row ids phase 2 gathers through
       {
-        const uint4 *src = reinterpret_cast<const uint4 *>(lmap + (int64_t)tile * kDtMap);
-        for (int e = lt; e < kDtMap * 2 / 16; e += NL) {
-          const uint4 v = __ldg(src + e);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lmap_b + e * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-        }
+        const uint16_t *src = lmap + (int64_t)tile * kDtMap;   // 6912 bytes, 16-byte aligned
+        for (int e = lt; e < kDtMap * 2 / 16; e += NL) cp_async16(lmap_b + e * 16, src + e * 8, 16u);
         if (lt < kDT) sorow[lt] = row0 + lt < n_rows ? __ldg(perm + row0 + lt) : -1;
         const int32_t *ids = halo_ids + (int64_t)tile * hcap;
         for (int h = lt; h < hn; h += NL) hids[h] = __ldg(ids + h);
       }
       dt_named_bar(2, NL);
-      // phase 2: gradient rows of the tile (B operand image) and halo rows of A (this CTA's 32 channels), rounded to TF32
+      // phase 2: gradient rows of the tile (B operand image) and halo rows of A (this CTA's 32 channels): every 16-byte
+      // copy of the tile is in flight at once (cp.async needs no registers), one global round trip for the whole tile
       for (int e = lt; e < kDT * cpr; e += NL) {
         const int r = e / cpr, c = e - r * cpr;
         const int row = sorow[r];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row >= 0) v = ldg_f4(G + (int64_t)row * ldg + c * 4);
-        dt_rna4(v);
-        sts_f4(g_b + (uint32_t)(c >> 3) * kBlkG + sw128_32b((uint32_t)r, (uint32_t)(c & 7)), v);
+        cp_async16(g_b + (uint32_t)(c >> 3) * kBlkG + sw128_32b((uint32_t)r, (uint32_t)(c & 7)),
+                   row >= 0 ? (const void *)(G + (int64_t)row * ldg + c * 4) : (const void *)G, row >= 0 ? 16u : 0u);
       }
       for (int e = lt; e < hn * 8; e += NL) {
         const int h = e >> 3, c = e & 7;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c * 4 < cvalid) v = ldg_f4(A + (int64_t)hids[h] * lda + cb * 32 + c * 4);
-        dt_rna4(v);
-        sts_f4(halo_b + (uint32_t)h * 128 + c * 16, v);
+        const bool ok = c * 4 < cvalid;
+        cp_async16(halo_b + (uint32_t)h * 128 + c * 16, ok ? (const void *)(A + (int64_t)hids[h] * lda + cb * 32 + c * 4) : (const void *)A,
+                   ok ? 16u : 0u);
+      }
+      cp_async_wait_all();
+      dt_named_bar(2, NL);
+      // the G tile is consumed by the tensor core as it lies: round it to the nearest TF32 in place (the A rows are
+      // rounded by the stage producers on their way through registers)
+      for (int e0 = lt; e0 < kDT * cpr; e0 += 4 * NL) {
+        float4 v[4];
+        uint32_t ad[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * NL;
+          const int r = e / cpr, c = e - r * cpr;
+          ad[u] = g_b + (uint32_t)(c >> 3) * kBlkG + sw128_32b((uint32_t)r, (uint32_t)(c & 7));
+          if (e < kDT * cpr) v[u] = dt_lds_f4(ad[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e0 + u * NL < kDT * cpr) {
+            dt_rna4(v[u]);
+            sts_f4(ad[u], v[u]);
+          }
+        }
       }
       // which 32-row chunks of which offsets hold any rule
       for (int idx = (lt >> 5); idx < 27 * 4; idx += kDtLoaders) {
@@ -216,21 +236,30 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int k = k0 + q;
-              for (int i = 0; i < rpw / 4; ++i) {
-                const int r = part_i * rpw + rl + 4 * i;     // row of the stage
-                const int rt = 32 * s + r;                   // row of the tile
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pres[q]) {
-                  const uint32_t slot = slmap[k * kDT + rt];
-                  if (slot < kDtOverflow) {
-                    v = dt_lds_f4(halo_b + slot * 128 + c * 16);
-                  } else if (slot == kDtOverflow) {          // beyond the halo capacity: through the global map (rare)
-                    const int idx = __ldg(nbr + (int64_t)sorow[rt] * 27 + k);
-                    if (c * 4 < cvalid) v = ldg_f4(A + (int64_t)idx * lda + cb * 32 + c * 4);
-                    dt_rna4(v);
+              // up to 4 rows per lane and M-block: all slots, then all loads, then all stores (independent chains)
+              uint32_t slot[4];
+              float4 v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rt = 32 * s + part_i * rpw + rl + 4 * i;
+                slot[i] = (pres[q] && i < rpw / 4) ? slmap[k * kDT + rt] : kDtAbsent;
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (slot[i] < kDtOverflow) v[i] = dt_lds_f4(halo_b + slot[i] * 128 + c * 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (i < rpw / 4) {
+                  const int r = part_i * rpw + rl + 4 * i;
+                  if (slot[i] == kDtOverflow) {              // beyond the halo capacity: through the global map (rare)
+                    const int idx = __ldg(nbr + (int64_t)sorow[32 * s + r] * 27 + k);
+                    if (c * 4 < cvalid) v[i] = ldg_f4(A + (int64_t)idx * lda + cb * 32 + c * 4);
                   }
+                  dt_rna4(v[i]);
+                  sts_f4(st_base + (uint32_t)q * kBlkA + sw128_32b((uint32_t)r, (uint32_t)c), v[i]);
                 }
-                sts_f4(st_base + (uint32_t)q * kBlkA + sw128_32b((uint32_t)r, (uint32_t)c), v);
               }
             }
             fence_proxy_async();

@@ -47,11 +47,13 @@ SIGNATURES = {
     "b200scn_prep_weight_tf32": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200scn_prep_weight_tf32_both": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "b200scn_scatter_conv": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
+    "b200scn_group_tiles": (_i32, [_vp, _i32, _i64, _vp, _vp]),
+    "b200scn_grouped_conv": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200scn_unpool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "b200scn_bn_forward": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _i64, _vp, _i32, _vp]),
-    "b200scn_bn_backward": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "b200scn_bn_backward": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200scn_bn_scratch_doubles": (_sz, [_i32]),
     "b200scn_input_features": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b200scn_input_features_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -45,8 +45,11 @@ class Level:
             self.nbr = alloc_rows(self.n, 27, dev, torch.int32)
             self.nbr_counts = torch.zeros(27, dtype=torch.int32, device=dev)
             st = _lib.stream_for(self.ukeys)
+            from . import ops as _ops
+            tok = _ops._p0("subm_map", "subm_map", 8.0 * self.n + 4.0 * 27 * self.n, 0, 0.0, 0.0)   # keys read + map written
             check(lib.b200scn_subm_map(ptr(self.ukeys), self.n, None, ptr(self.hkeys), ptr(self.hvals), self.cap,
                                        self.size, ptr(self.nbr), ptr(self.nbr_counts), st))
+            _ops._p1(tok)
             # rule counts travel to the host asynchronously; nobody waits for them unless the op counters
             # are read or a weight gradient needs exact pair-list sizes (long after this point)
             self._counts_host = torch.empty(27, dtype=torch.int32, pin_memory=True)
@@ -87,17 +90,22 @@ class TilePlan:
         # curve keys live in a quantised-capacity buffer padded with +inf keys, so that the sort (torch's radix sort --
         # plumbing) and its outputs have sizes that repeat from step to step (see _lib.round_rows) and padding sorts last
         cap = _lib.round_rows(max(n, 1))
+        from . import ops as _ops
+        tok = _ops._p0("morton_sort", "morton_keys+sort", 8.0 * n + 8.0 * n + 4.0 * n, 0, 0.0, 0.0)
         mk = torch.full((cap,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
         check(lib.b200scn_morton_keys(ptr(level.ukeys), n, ptr(mk), st))
         self.perm = torch.sort(mk)[1].to(torch.int32)[:n]   # keys are unique; b < 2^15 keeps them positive
+        _ops._p1(tok)
         T = (n + 127) // 128
         self.hcap = hcap
         self.lmap = alloc_flat(T * 27 * 128, dev, torch.int16)
         self.halo_ids = alloc_flat(T * hcap, dev, torch.int32)
         self.halo_n = alloc_flat(T, dev, torch.int32)
         self.kmask = alloc_flat(T, dev, torch.int32)
+        tok = _ops._p0("tile_plan", "tile_plan", 4.0 * 27 * n + 4.0 * n + 2.0 * 27 * T * 128 + 4.0 * T * hcap, 0, 0.0, 0.0)
         check(lib.b200scn_tile_plan(ptr(nbr), ptr(self.perm), n, hcap, ptr(self.lmap), ptr(self.halo_ids),
                                     ptr(self.halo_n), ptr(self.kmask), st))
+        _ops._p1(tok)
 
 
 def build_pairs(map_t, n, K, total, order=None):
@@ -110,8 +118,11 @@ def build_pairs(map_t, n, K, total, order=None):
     pair_in = alloc_flat(max(total, 1), dev, torch.int32)
     pair_out = alloc_flat(max(total, 1), dev, torch.int32)
     st = _lib.stream_for(map_t)
+    from . import ops as _ops
+    tok = _ops._p0("pair_lists", "pair_lists", 2.0 * 4.0 * K * n + 8.0 * total, 0, 0.0, 0.0)   # map read twice + pairs written
     check(lib.b200scn_pair_lists_ordered(ptr(map_t), ptr(order), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets),
                                          ptr(scratch), nbytes, st))
+    _ops._p1(tok)
     return pair_in, pair_out, offsets
 
 
@@ -122,7 +133,7 @@ class Down:
         self.s, self.K, self.fine, self.coarse, self.parent, self.off = s, s ** 3, fine, coarse, parent, off
         self.child = None
         self.pairs = None
-        self.onehot = None
+        self.gtab = None
 
     def child_map(self):
         if self.child is None:
@@ -133,15 +144,17 @@ class Down:
                                         ptr(self.child), self.coarse.n, st))
         return self.child
 
-    def onehot_map(self):
-        """fine-side view of the same rulebook: onehot[i][k] = parent[i] if off[i] == k else -1, so that
-        out[i] = in[parent[i]] @ W[off[i]] runs through the output-stationary gather kernel (tensor-core path)."""
-        if self.onehot is None:
-            oh = alloc_rows(self.fine.n, self.K, self.parent.device, torch.int32)
-            oh.fill_(-1)
-            oh.scatter_(1, self.off.long().unsqueeze(1), self.parent.unsqueeze(1))
-            self.onehot = oh
-        return self.onehot
+    def group_tiles(self):
+        """Tile table of the offset-sorted rulebook for the fine-side tensor-core convolutions (b200scn_grouped_conv):
+        (fine ids, coarse ids, table, max_tiles); built once per step and shared by Deconvolution forward and
+        Convolution backward-input."""
+        if self.gtab is None:
+            pin, pout, offs = self.child_pairs()
+            max_tiles = (self.fine.n + 127) // 128 + self.K
+            tab = alloc_flat(4 * max_tiles, self.parent.device, torch.int32)
+            check(lib.b200scn_group_tiles(ptr(offs), self.K, max_tiles, ptr(tab), _lib.stream_for(self.parent)))
+            self.gtab = (pin, pout, tab, max_tiles)
+        return self.gtab
 
     def child_pairs(self):
         """pair_in = fine ids, pair_out = coarse ids, grouped by offset."""
@@ -180,6 +193,9 @@ class Metadata:
         nlev = len(sizes)
         # header: [err, n_0, n_1, ..., n_{nlev-1}]
         hdr = torch.zeros(1 + nlev, dtype=i32, device=device)
+        from . import ops as _ops
+        # algorithmic bytes: 32 P coords read + 4 P ids written; the coarse levels re-hash <= P keys each
+        tok = _ops._p0("grid_build", "pack_coords+hash+scan (all levels)", 36.0 * P, 0, 0.0, 0.0)
         check(lib.b200scn_pack_coords(ptr(coords), P, coords.shape[1], int(spatial_size), ptr(keys), ptr(hdr), st))
         cap = lib.b200scn_hash_capacity(Pc)
         sbytes = lib.b200scn_grid_scratch_bytes(Pc)
@@ -209,6 +225,7 @@ class Metadata:
             check(lib.b200scn_grid_build(ptr(ckeys), P, n_dev, ptr(ck), ptr(cv), cap, ptr(parent), ptr(cu),
                                          None, None, None, hdr[li + 1:].data_ptr(), ptr(scratch), sbytes, st))
             raw.append((cu, ck, cv, parent, off))
+        _ops._p1(tok)
         host = hdr.cpu()  # the one host sync of the forward
         self.syncs += 1
         if int(host[0]) != 0:

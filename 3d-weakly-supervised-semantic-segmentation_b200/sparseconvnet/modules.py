@@ -111,10 +111,17 @@ class Sequential(torch.nn.Sequential):
         while i < len(mods):
             m = mods[i]
             if i + 1 < len(mods) and _fusable_residual(m, mods[i + 1]):
-                skip = m._modules["0"](input)
                 branch = list(m._modules["1"]._modules.values())
                 y = input
-                for j, mod in enumerate(branch[:-1]):
+                if isinstance(branch[0], BatchNormalization) and len(branch) > 1 and input.features.requires_grad:
+                    # x feeds the BatchNorm AND the skip: one function returns both, so that backward sums the two
+                    # gradients inside the BatchNorm backward kernel
+                    y, input = branch[0].forward_with_alias(input, _bn_feeds_conv(branch[0], branch[1]))
+                    rest = list(enumerate(branch[:-1]))[1:]
+                else:
+                    rest = list(enumerate(branch[:-1]))
+                skip = m._modules["0"](input)
+                for j, mod in rest:
                     y = mod(y, feeds_conv=True) if _bn_feeds_conv(mod, branch[j + 1]) else mod(y)
                 input = branch[-1](y, addend=skip.features)
                 i += 2
@@ -151,7 +158,9 @@ class ConcatTable(Sequential):
 class AddTable(Module):
     def forward(self, input):
         out = SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size)
+        tok = ops._p0("add", "torch add (AddTable)", 12.0 * input[0].features.nelement() * (len(input) - 1), 0, 0.0, 0.0)
         out.features = sum(i.features for i in input)
+        ops._p1(tok)
         return out
 
     def input_spatial_size(self, out_size):
@@ -161,7 +170,9 @@ class AddTable(Module):
 class JoinTable(Module):
     def forward(self, input):
         out = SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size)
+        tok = ops._p0("join", "torch cat (JoinTable)", 8.0 * sum(i.features.nelement() for i in input), 0, 0.0, 0.0)
         out.features = torch.cat([i.features for i in input], 1)
+        ops._p1(tok)
         return out
 
     def input_spatial_size(self, out_size):
@@ -447,6 +458,15 @@ class BatchNormalization(Module):
                                              self.running_var, self.eps, self.momentum, self.training,
                                              self.leakiness, feeds_conv)
         return out
+
+    def forward_with_alias(self, input, feeds_conv=False):
+        """-> (bn(input), input'): input' carries the same features; gradients flowing back into it are summed with the
+        BatchNorm's own input gradient in one kernel (ops.BatchNormSkipFn)."""
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
+        y, xa = ops.BatchNormSkipFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
+                                          self.eps, self.momentum, self.training, self.leakiness, feeds_conv)
+        return (SparseConvNetTensor(y, input.metadata, input.spatial_size),
+                SparseConvNetTensor(xa, input.metadata, input.spatial_size))
 
     def input_spatial_size(self, out_size):
         return out_size

@@ -209,13 +209,21 @@ def gather_conv(x, map_t, n_out, K, gw, addend=None, rules=None):
 
 def scatter_conv(x, map_t, n_out, K, gw, down=None):
     """out[map[j,k]] = x[j] @ Wg[k]; every out row is addressed exactly once by a strided child map.
-    On the tensor-core path the same product is computed output-stationary through the one-hot fine-side map."""
+    On the tensor-core path the rules are taken offset-sorted (the scn-form rulebook) and every run of <= 128 rules of one
+    offset is one dense tile (b200scn_grouped_conv)."""
     x, ldx = _c(x)
-    if down is not None and _use_tf32(gw, ldx, x):
-        return gather_conv(x, down.onehot_map(), n_out, K, gw, rules=n_out)
-    w = gw.rowmajor()
     Cin, Cout = gw.cin, gw.cout
     out = alloc_rows(n_out, Cout, x.device)
+    if down is not None and _use_tf32(gw, ldx, x):
+        fine_ids, coarse_ids, tab, max_tiles = down.group_tiles()
+        w = gw.kmajor()
+        tok = _p0("grouped%d" % K, "grouped_conv", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
+                  n_out, 8.0, 2.0 * Cin * Cout)
+        check(lib.b200scn_grouped_conv(ptr(x), ldx, ptr(coarse_ids), ptr(fine_ids), ptr(tab), max_tiles, n_out, K, ptr(w),
+                                       Cin, Cout, ptr(out), Cout, _lib.stream_for(x)))
+        _p1(tok)
+        return out
+    w = gw.rowmajor()
     tok = _p0("scatter%d" % K, "conv_scatter", 4.0 * (x.shape[0] * Cin + n_out * Cout) + 4.0 * K * Cin * Cout,
               n_out, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_scatter_conv(ptr(x), ldx, ptr(map_t), x.shape[0], K, ptr(w), Cin, Cout, ptr(out), Cout,
@@ -356,7 +364,9 @@ class UnPoolingFn(torch.autograd.Function):
         x, ldx = _c(x)
         C = x.shape[1]
         out = alloc_rows(down.fine.n, C, x.device)
+        tok = _p0("unpool", "unpool", 4.0 * (down.fine.n + down.coarse.n) * C + 4.0 * down.fine.n, 0, 0.0, 0.0)
         check(lib.b200scn_unpool(ptr(x), ldx, ptr(down.parent), down.fine.n, C, ptr(out), C, _lib.stream_for(x)))
+        _p1(tok)
         return out
 
     @staticmethod
@@ -365,8 +375,10 @@ class UnPoolingFn(torch.autograd.Function):
         g, ldg = _c(g)
         C = g.shape[1]
         dx = alloc_rows(down.coarse.n, C, g.device)
+        tok = _p0("unpool_bwd", "unpool_bwd", 4.0 * (down.fine.n + down.coarse.n) * C + 4.0 * down.fine.n, 0, 0.0, 0.0)
         check(lib.b200scn_unpool_bwd(ptr(g), ldg, ptr(down.child_map()), down.coarse.n, down.K, C, ptr(dx), C,
                                      _lib.stream_for(g)))
+        _p1(tok)
         return dx, None
 
 
@@ -404,45 +416,75 @@ def bn_scratch(device):
     return buf
 
 
+def _bn_forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32):
+    x, ldx = _c(x)
+    n, C = x.shape
+    dev = x.device
+    y = alloc_rows(n, C, dev)
+    save_mean = torch.empty(C, dtype=torch.float32, device=dev)
+    save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
+    scratch = bn_scratch(dev)
+    tok = _p0("bn_fwd", "bn", 12.0 * n * C, 0, 0.0, 0.0)
+    check(lib.b200scn_bn_forward(ptr(x), ldx, n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
+                                 ptr(save_mean), ptr(save_invstd), eps, momentum, 1 if train else 0, leak,
+                                 ptr(y), C, ptr(scratch), 1 if (round_tf32 and _precision[0] == 1) else 0,
+                                 _lib.stream_for(x)))
+    _p1(tok)
+    ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
+    ctx.leak, ctx.train = leak, bool(train)
+    return y
+
+
+def _bn_backward(ctx, g, addend):
+    x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
+    x, ldx = _c(x)
+    g, ldg = _c(g)
+    n, C = x.shape
+    dev = x.device
+    lda = 0
+    if addend is not None:
+        addend, lda = _c(addend)
+    dx = alloc_rows(n, C, dev)
+    dweight = torch.empty(C, dtype=torch.float32, device=dev)
+    dbias = torch.empty(C, dtype=torch.float32, device=dev)
+    scratch = bn_scratch(dev)
+    tok = _p0("bn_bwd", "bn", (24.0 if addend is not None else 20.0) * n * C, 0, 0.0, 0.0)
+    check(lib.b200scn_bn_backward(ptr(x), ldx, ptr(g), ldg, n, C, ptr(weight), ptr(bias), ptr(save_mean),
+                                  ptr(save_invstd), ctx.leak, 1 if ctx.train else 0, ptr(addend), lda, ptr(dx), C,
+                                  ptr(dweight), ptr(dbias), ptr(scratch), _lib.stream_for(x)))
+    _p1(tok)
+    return dx, dweight, dbias
+
+
 class BatchNormFn(torch.autograd.Function):
     """scn.BatchNormReLU / BatchNormLeakyReLU (models/SparseConvNet.py:69,116,118,136):
     BatchNormalization_updateOutput / _backward (eps 1e-4, momentum 0.9 on the old value, App. B.8)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32=False):
-        x, ldx = _c(x)
-        n, C = x.shape
-        dev = x.device
-        y = alloc_rows(n, C, dev)
-        save_mean = torch.empty(C, dtype=torch.float32, device=dev)
-        save_invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        scratch = bn_scratch(dev)
-        tok = _p0("bn_fwd", "bn", 12.0 * n * C, 0, 0.0, 0.0)
-        check(lib.b200scn_bn_forward(ptr(x), ldx, n, C, ptr(weight), ptr(bias), ptr(running_mean), ptr(running_var),
-                                     ptr(save_mean), ptr(save_invstd), eps, momentum, 1 if train else 0, leak,
-                                     ptr(y), C, ptr(scratch), 1 if (round_tf32 and _precision[0] == 1) else 0,
-                                     _lib.stream_for(x)))
-        _p1(tok)
-        ctx.save_for_backward(x, weight, bias, save_mean, save_invstd)
-        ctx.leak, ctx.train = leak, bool(train)
-        return y
+        return _bn_forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32)
 
     @staticmethod
     def backward(ctx, g):
-        x, weight, bias, save_mean, save_invstd = ctx.saved_tensors
-        x, ldx = _c(x)
-        g, ldg = _c(g)
-        n, C = x.shape
-        dev = x.device
-        dx = alloc_rows(n, C, dev)
-        dweight = torch.empty(C, dtype=torch.float32, device=dev)
-        dbias = torch.empty(C, dtype=torch.float32, device=dev)
-        scratch = bn_scratch(dev)
-        tok = _p0("bn_bwd", "bn", 20.0 * n * C, 0, 0.0, 0.0)
-        check(lib.b200scn_bn_backward(ptr(x), ldx, ptr(g), ldg, n, C, ptr(weight), ptr(bias), ptr(save_mean),
-                                      ptr(save_invstd), ctx.leak, 1 if ctx.train else 0, ptr(dx), C, ptr(dweight),
-                                      ptr(dbias), ptr(scratch), _lib.stream_for(x)))
-        _p1(tok)
+        dx, dweight, dbias = _bn_backward(ctx, g, None)
+        return dx, dweight, dbias, None, None, None, None, None, None, None
+
+
+class BatchNormSkipFn(torch.autograd.Function):
+    """BatchNorm at the head of a residual branch: returns (bn(x), x).  The second output IS x, handed to the skip
+    connection; in backward the gradient that comes back through it is added inside the BatchNorm backward kernel
+    (one pass) instead of by an autograd add kernel over the whole tensor (26 such adds per step in the m=32 UNet)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32=False):
+        y = _bn_forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leak, round_tf32)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g, gskip):
+        if g is None:   # only the skip was used
+            return gskip, None, None, None, None, None, None, None, None, None
+        dx, dweight, dbias = _bn_backward(ctx, g, gskip)
         return dx, dweight, dbias, None, None, None, None, None, None, None
 
 
@@ -456,8 +498,10 @@ class InputFeaturesFn(torch.autograd.Function):
             raise TypeError("InputLayer: features must be float32, got %s" % feats.dtype)
         P, C = feats.shape
         out = alloc_rows(n0, C, feats.device, zero=True)
+        tok = _p0("input_feats", "input_features", 4.0 * (P + n0) * C + 4.0 * P, 0, 0.0, 0.0)
         check(lib.b200scn_input_features(ptr(feats), P, C, ptr(md.pv), ptr(md.count), ptr(md.first_row),
                                          ptr(md.last_row), md.mode, ptr(out), _lib.stream_for(feats)))
+        _p1(tok)
         ctx.md = md
         return out
 
@@ -480,8 +524,10 @@ class OutputFeaturesFn(torch.autograd.Function):
         feats, ldf = _c(feats)
         C = feats.shape[1]
         out = alloc_rows(md.P, C, feats.device)
+        tok = _p0("output_feats", "output_features", 4.0 * (feats.shape[0] + md.P) * C + 4.0 * md.P, 0, 0.0, 0.0)
         check(lib.b200scn_output_features(ptr(feats), ldf, md.P, C, ptr(md.pv), ptr(md.first_row), ptr(md.last_row),
                                           md.mode, ptr(out), _lib.stream_for(feats)))
+        _p1(tok)
         ctx.md, ctx.n = md, feats.shape[0]
         return out
 
@@ -492,9 +538,11 @@ class OutputFeaturesFn(torch.autograd.Function):
         C = g.shape[1]
         d = alloc_rows(ctx.n, C, g.device)
         start, rows = md.site_rows()
+        tok = _p0("output_feats_bwd", "output_features_bwd", 4.0 * (ctx.n + md.P) * C + 4.0 * md.P, 0, 0.0, 0.0)
         check(lib.b200scn_output_features_bwd_csr(ptr(g), ctx.n, C, ptr(start), ptr(md.count), ptr(rows),
                                                   ptr(md.first_row), ptr(md.last_row), md.mode, ptr(d), C,
                                                   _lib.stream_for(g)))
+        _p1(tok)
         return d, None
 
 

@@ -31,11 +31,30 @@ DEFAULT_CONFIG = "cfg3_unet_m32_r2_res_s50_b5"
 
 
 def _peaks():
+    """-> (hbm GB/s, source, tf32 TFLOP/s dict).  TF32 dense peak = half the measured bf16 cuBLAS throughput: tcgen05.mma
+    kind::tf32 issues M128 x N x K8 in N/2 cycles = 4096 flop/clk/SM, half of kind::f16 (own microbenchmark,
+    profiles/r1_mma_issue_microbench.txt: 16.5 / 32.3 / 64.0 / 127.4 cycles for N = 32 / 64 / 128 / 256)."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
+            d = json.load(f)
+        tf32 = {"burst": float(d["bf16_tflops"]) / 2, "sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2,
+                "source": "0.5 x measured bf16 (MEASURED_PEAKS.json)"}
+        return float(d["hbm_gbs"]), "measured", tf32
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)", {"burst": 1125.0, "sustained": 1125.0, "source": "nominal 2.25 PF bf16 / 2"}
+
+
+def _ncu_traffic(kernel):
+    """DRAM bytes of one launch of the dominant kernel from the COMMITTED ncu --set full capture (profiles/r2_dominant_ncu.json,
+    written by tools/ncu_summary.py from the raw CSV page); None when no capture of this kernel is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dominant_ncu.json")) as f:
+            d = json.load(f)
+        if d.get("bench_kernel") == kernel:
+            return d
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -105,6 +124,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)   # torch.distributed.run exports OMP_NUM_THREADS=1: use every host core anyway
     from b200scn_synth import CONFIGS, build_encoder
     from oracle import scn_oracle as ref
     kind, m, reps, res, scale, batch = CONFIGS[args.config]
@@ -149,6 +169,7 @@ def cpu_baseline_sample(cfg, n_points, budget_s=25.0):
     """Oracle port timed on the host cores: 1 scene of the workload, fwd+bwd, as many steps as fit the budget (>=1)."""
     from b200scn_synth import CONFIGS, build_encoder, make_batch
     from oracle import scn_oracle as ref
+    torch.set_num_threads(os.cpu_count() or 1)
     kind, m, reps, res, scale, batch = CONFIGS[cfg]
     torch.manual_seed(0)
     net = build_encoder(ref, kind, m, reps, res)
@@ -205,8 +226,33 @@ def run_b200(args):
     stats = {"voxels": 0}
 
     debug = os.environ.get("B200SCN_BENCH_DEBUG") == "1"
+    from b200scn_synth import EVAL_REPS
+    eval_reps = EVAL_REPS.get(args.config, 0)
+    if eval_reps:
+        net.eval()
+    comm = {"ms": 0.0, "n": 0}
+
+    def eval_step(i, from_host):
+        # validation as the reference runs it (validation.py:37-57: val_reps passes, a fresh transform each): forward only,
+        # every pass rebuilds all rulebooks; the result read back is the mean logit of the last pass
+        with torch.no_grad():
+            for r in range(eval_reps):
+                j = (i * eval_reps + r) % n_distinct
+                if from_host:
+                    c, f = pinned[j]
+                    coords, feats = c.to(dev, non_blocking=True), f.to(dev, non_blocking=True)
+                else:
+                    coords, feats = resident[j]
+                x = net[0]([coords, feats])
+                stats["voxels"] += x.features.shape[0]
+                y = x
+                for mod in list(net)[1:]:
+                    y = mod(y)
+            return y.mean()
 
     def step(i, from_host):
+        if eval_reps:
+            return eval_step(i, from_host)
         t_start = time.perf_counter()
         if from_host:
             c, f = pinned[i % n_distinct]
@@ -227,6 +273,7 @@ def run_b200(args):
         loss.backward()
         if world > 1:
             flat.allreduce_mean()
+            comm["pending"] = True
         opt.step()
         if debug:
             t_end = time.perf_counter()
@@ -251,33 +298,49 @@ def run_b200(args):
         if prof:
             scn_ops.profile_reserve(800 * args.steps)
             scn_ops.profile_begin()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        # one event per step boundary: total = e[0] -> e[K] (EXACTLY K steps), and per-step times for the median
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        comm["ms"], comm["n"] = 0.0, 0
+        ev[0].record()
         for i in range(args.steps):
             loss = step(args.warmup + i, from_host)
             # D2H read of the step's result, every step in both arms: a training loop logs its loss, and without it the
             # host runs a step ahead, two steps' activations are alive at once and the caching allocator occasionally
             # grows (cudaMalloc + implicit sync, ~0.1-0.2 s) inside the timed region
             loss_host = loss.item()  # noqa: F841
+            ev[i + 1].record()
+            if comm.pop("pending", False):     # the step is complete (loss.item() synchronised): read the exposed-wait timer
+                comm["ms"] += flat.exposed_ms()
+                comm["n"] += 1
             if sampler is not None and (i % 6 == 3 or (args.steps <= 3 and i == args.steps - 1)):
                 sampler.sample()
-        e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         gc.enable()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[-1])
+        per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+        median = per_step[len(per_step) // 2]
         prof_out = scn_ops.profile_end() if prof else None
         t = torch.tensor([ms, float(stats["voxels"])], dtype=torch.float64, device=dev)
+        extra = {"median_ms": median, "min_ms": per_step[0], "max_ms": per_step[-1],
+                 "comm_exposed_ms": comm["ms"] / comm["n"] if comm["n"] else 0.0}
         if world > 1:
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            # per-rank step time and exposed collective wait: names the scaling limiter (imbalance vs communication)
+            mine = torch.tensor([ms / args.steps, extra["comm_exposed_ms"], float(stats["voxels"]) / args.steps],
+                                dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            extra["per_rank"] = [{"ms_per_step": float(a[0]), "comm_exposed_ms": float(a[1]), "voxels_per_step": float(a[2])}
+                                 for a in allr]
             ms, vox = float(tmax[0]), float(t[1])
         else:
             vox = float(t[1])
-        return ms, vox, scn.launch_count() - launches0, prof_out
+        return ms, vox, scn.launch_count() - launches0, prof_out, extra
 
     # allocator priming (untimed, before any warm-up): site counts differ per batch, so torch's caching allocator needs to
     # have met every distinct batch before its block pool stops growing (cudaMalloc inside a step synchronises): whole
@@ -298,49 +361,78 @@ def run_b200(args):
         # one discarded rehearsal of the timed loop: whatever still grows on first use of this exact call sequence (caching
         # allocator blocks: observed as a 0.1-0.25 s stall of one step in the first timed loop of ~1 run in 3) happens here
         timed(False, False)
-        ms, vox, launches, _ = timed(False, False, clk)         # headline: device-resident inputs, nothing but the step
+        ms, vox, launches, _, ex = timed(False, False, clk)     # headline: device-resident inputs, nothing but the step
     clocks = clk.summary()
-    ms_e, vox_e, _, _ = timed(True, False)                 # end to end: pinned host inputs, H2D inside, loss read back
-    # roofline pass: the same K steps again with CUDA events around every conv / BN launch (kept out of the headline
-    # timing because recording ~700 event pairs per step costs a few ms of host time)
-    ms_p, _, _, prof = timed(False, True)
+    ms_e, vox_e, _, _, ex_e = timed(True, False)           # end to end: pinned host inputs, H2D inside, loss read back
+    # roofline pass: the same K steps again with CUDA events around every library launch (kept out of the headline
+    # timing because recording ~900 event pairs per step costs a few ms of host time)
+    ms_p, _, _, prof, _ = timed(False, True)
 
     if rank == 0:
-        peak, which = _peaks()
+        peak, which, tf32_peak = _peaks()
         h2d = sum(c.numel() * 8 + f.numel() * 4 for c, f in pinned) / len(pinned)
         roof = None
-        # the dominant kernel: the tiled submanifold kernel ("tiled27") wherever it runs, else the gather kernel
-        dom = max((k for k in ("tiled27", "gather27") if prof and prof.get(k)), key=lambda k: prof[k]["ms"], default=None)
+        conv_kinds = [k for k in (prof or {}) if k.startswith(("tiled", "gather", "scatter", "pair_dw", "tile_dw"))]
+        # the dominant kernel = the kind with the most GPU time among the convolution kernels
+        dom = max(conv_kinds, key=lambda k: prof[k]["ms"], default=None)
         if dom:
             g = prof[dom]
             ach = g["bytes"] / (g["ms"] * 1e-3) / 1e9
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed ncu --set full
-            # capture (profiles/r1_halo_ncu_details.txt): the level-1 64->64 SubmanifoldConvolution forward of this
-            # workload (tiled kernel), 135.2 MB read + 64.5 MB written against 241.8 MB algorithmic -- no re-read beyond the
-            # compulsory traffic (part of the input is still L2-resident from the producing kernel).
-            traffic = {"bytes": 199.6e6, "launch": "level-1 SubM 64->64 fwd, 411829 sites", "algorithmic_bytes": 241.8e6}
-            roof = {"bound": "hbm", "kernel": g["kernel"], "achieved": ach, "peak": peak, "peak_source": which, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic["bytes"], "traffic_detail": traffic, "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / g["n"],
+            cap = _ncu_traffic(g["kernel"])   # committed ncu --set full capture of ONE launch of this kernel, or None
+            by_kind = {}
+            for k, v in prof.items():
+                sec = v["ms"] * 1e-3
+                e = {"kernel": v["kernel"], "ms_per_step": v["ms"] / args.steps, "n_per_step": v["n"] / args.steps,
+                     "GBps": v["bytes"] / sec / 1e9 if sec else None, "hbm_frac": v["bytes"] / sec / 1e9 / peak if sec else None}
+                if v["flops"]:
+                    e["TFLOPs"] = v["flops"] / sec / 1e12
+                    e["tensor_frac"] = e["TFLOPs"] / tf32_peak["sustained"]
+                by_kind[k] = e
+            conv_ms = sum(prof[k]["ms"] for k in conv_kinds)
+            conv_bytes = sum(prof[k]["bytes"] for k in conv_kinds)
+            conv_flops = sum(prof[k]["flops"] for k in conv_kinds)
+            all_bytes = sum(v["bytes"] for v in prof.values())
+            all_ms = sum(v["ms"] for v in prof.values())
+            roof = {"bound": "hbm", "kernel": g["kernel"], "kind": dom, "achieved": ach, "peak": peak, "peak_source": which,
+                    "unit": "GB/s", "frac": ach / peak,
+                    "traffic": cap["dram_bytes"] if cap else None, "traffic_detail": cap,
+                    "launches": g["n"], "avg_launch_us": 1e3 * g["ms"] / g["n"],
                     "algorithmic_bytes_per_launch": g["bytes"] / g["n"], "tflops": g["flops"] / (g["ms"] * 1e-3) / 1e12,
-                    "share_of_step": g["ms"] / ms_p, "profiled_ms_per_step": ms_p / args.steps, "by_kind": {k: {"ms_per_step": v["ms"] / args.steps, "n_per_step": v["n"] / args.steps,
-                                                                 "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
-                                                                 "TFLOPs": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else None}
-                                                             for k, v in prof.items()}}
+                    "tensor_frac": g["flops"] / (g["ms"] * 1e-3) / 1e12 / tf32_peak["sustained"], "tf32_peak_tflops": tf32_peak,
+                    "share_of_step": g["ms"] / ms_p, "profiled_ms_per_step": ms_p / args.steps,
+                    # second half of the metric ("conv HBM GB/s"): algorithmic bytes of every convolution kernel (SubM, strided,
+                    # NiN; forward, backward-input, weight gradient) over their summed kernel time
+                    "conv_hbm_gbs": conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms else None,
+                    "conv_hbm_frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / peak if conv_ms else None,
+                    "conv_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
+                    "conv_ms_per_step": conv_ms / args.steps,
+                    # whole step against the HBM roofline: algorithmic bytes of EVERY profiled library call of the step
+                    # (live N_l, R_l of this run, SURVEY 8d formulas) over the headline step time
+                    "step_algorithmic_gb": all_bytes / args.steps / 1e9,
+                    "step_hbm_frac": all_bytes / args.steps / 1e9 / (ms / args.steps * 1e-3) / peak,
+                    "step_kernel_ms_profiled": all_ms / args.steps,
+                    "by_kind": by_kind}
+        step_desc = ("eval: %d forward passes (fresh coordinates, all rulebooks rebuilt each pass), no_grad" % eval_reps) if eval_reps \
+            else "InputLayer(hash+rulebooks, fresh coords)+fwd+loss+bwd(dI,dW)+allreduce+fused Adam"
         line = {
             "metric": METRIC, "value": vox / (ms * 1e-3), "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_median": ex["median_ms"],
+            "ms_per_step_min_max": [ex["min_ms"], ex["max_ms"]], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": args.config, "encoder": "%s m=%d block_reps=%d residual=%s" % (kind, m, reps, res),
                        "scale": scale, "batch_per_gpu": batch, "points_per_scene": args.points,
                        "voxels_per_step_per_gpu": vox / args.steps / world, "parallelism": "dp%d" % world,
-                       "step": "InputLayer(hash+rulebooks, fresh coords)+fwd+loss+bwd(dI,dW)+allreduce+fused Adam",
+                       "step": step_desc,
                        "l2": "inputs larger than L2: >1 GB of activations per step, fresh coordinates each step"},
             "clocks": clocks,
             "e2e": {"value": vox_e / (ms_e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e / args.steps,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+                    "ms_per_step_median": ex_e["median_ms"], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": roof,
         }
+        if world > 1:
+            line["comm_exposed_ms"] = ex["comm_exposed_ms"]
+            line["per_rank"] = ex.get("per_rank")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args.config, args.points)
         print(json.dumps(line), flush=True)

@@ -135,6 +135,17 @@ int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transpose
 int b200scn_prep_weight_tf32_both(const float *w0, int K, int a, int b, int flip_bwd, float *out_fwd, float *out_bwd,
                                   void *stream);
 
+/* Offset-sorted ("grouped") strided convolution on the tensor cores, for the directions in which every output row has
+ * exactly one rule (Deconvolution_updateOutput, backward-input of Convolution): the scn-form rulebook
+ * (in_rows[p], out_rows[p], offsets[K+1], rules sorted by offset) is cut into runs of <= 128 rules of ONE offset
+ * (b200scn_group_tiles: tab[4*t] = {offset, first rule, rules, 0}, max_tiles >= ceil(n/128) + K entries), and each run is
+ * one dense [rules x Cin] . W[offset] tile: out[out_rows[p],:] = A[in_rows[p],:] . W[k(p)].  TF32 operand Wkm as for
+ * b200scn_gather_conv(precision = 1). */
+int b200scn_group_tiles(const int32_t *offsets_dev, int K, int64_t max_tiles, int32_t *tab, void *stream);
+int b200scn_grouped_conv(const float *A, int64_t lda, const int32_t *in_rows, const int32_t *out_rows,
+                         const int32_t *tab, int64_t max_tiles, int64_t n_out, int K, const float *Wkm, int Cin,
+                         int Cout, float *out, int64_t ldo, void *stream);
+
 /* out[map[j*K+k],:] = A[j,:] . W[k] for every present (j,k)   (Deconvolution_updateOutput,
  * Convolution backward-input).  Rows of `out` not addressed by map are left untouched. */
 int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_t n_in, int K,
@@ -171,11 +182,12 @@ int b200scn_bn_forward(const float *x, int64_t ldx, int64_t n, int C, const floa
                        float *y, int64_t ldy, double *scratch, int round_tf32, void *stream);
 /* BatchNormalization_backward; the ReLU mask is recomputed from x, which equals the sign of the forward output bit for
  * bit.  train != 0: batch-statistics formula; train == 0 (forward used the running statistics, which do not depend on x):
- * d_in = g * invstd * weight, d_weight / d_bias from the same sums. */
+ * d_in = g * invstd * weight, d_weight / d_bias from the same sums.  addend (may be NULL): added to d_in in the same pass --
+ * the gradient that reaches x through its other consumer (the skip of a residual block), instead of a separate add kernel. */
 int b200scn_bn_backward(const float *x, int64_t ldx, const float *dy, int64_t lddy, int64_t n, int C,
                         const float *weight, const float *bias, const float *save_mean,
-                        const float *save_invstd, float leak, int train, float *dx, int64_t lddx,
-                        float *d_weight, float *d_bias, double *scratch, void *stream);
+                        const float *save_invstd, float leak, int train, const float *addend, int64_t ldadd,
+                        float *dx, int64_t lddx, float *d_weight, float *d_bias, double *scratch, void *stream);
 
 /* ------------------------------------------------------------------ I/O layers (A1, A9) */
 /* InputLayer_updateOutput feature half: out[pv[r]] += mult(r)*feats[r]; mode 1 last, 2 first, 3 sum,
