@@ -152,10 +152,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const
 // fp32 -> nearest TF32 (ties away), in place.  tcgen05.mma kind::tf32 TRUNCATES its operands to a 10-bit mantissa: a
 // one-sided error of up to 2^-10 whose mean (~3.5e-4 relative) does not average out over the reduction -- measured as a
 // coherent ~5e-4 per truncated operand in the per-op parity tests.  Rounding here makes the error zero-mean.
+// Done with two full-rate integer instructions (add half an ulp of the 10-bit mantissa to the magnitude, clear the low 13
+// bits: exactly cvt.rna.tf32.f32 for finite values) -- the conversion instruction itself issues at 16 lanes/clk/SM and
+// 32 of them per row and stage would saturate that pipe.
 __device__ __forceinline__ float rna1(float v) {
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-  return __uint_as_float(t);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void rna4(float4 &v) { v.x = rna1(v.x); v.y = rna1(v.y); v.z = rna1(v.z); v.w = rna1(v.w); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -206,7 +207,8 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
                     const uint16_t *__restrict__ lmap, const int32_t *__restrict__ halo_ids,
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
-                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int pf_dist, int w_rows_per_k, int w_row0) {
+                    int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int pf_dist, int w_rows_per_k, int w_row0,
+                    int round_a) {
   constexpr int NPW = 4 * NS;
   constexpr int NTHREADS = 32 * (NPW + 2);
   extern __shared__ uint8_t smem_raw[];
@@ -361,7 +363,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
             a3 = ldg_f4(src + 12);
           }
         }
-        rna4(a0); rna4(a1); rna4(a2); rna4(a3);
+        if (round_a) { rna4(a0); rna4(a1); rna4(a2); rna4(a3); }   // (skipped when the producer already rounded the rows)
       };
       auto prefetch = [&](int v2_) {
         const int ki = 2 * (v2_ - kb * nk2);
@@ -535,7 +537,7 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
                        const int32_t *nbr, const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids,
                        const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin,
                        int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k,
-                       int w_row0, cudaStream_t st) {
+                       int w_row0, int round_a, cudaStream_t st) {
   auto kern = halo_conv_tc_kernel<NT, NS, MINB>;
   static int smem_set = 0;   // per template instantiation: the attribute only ever needs to grow
   if ((int)L.total > smem_set) {
@@ -548,14 +550,14 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
   const int pf_dist = g_opt.halo_pf >= 0 ? g_opt.halo_pf : kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
   kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
                                                             (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,
-                                                            acc_cols, pf_dist, w_rows_per_k, w_row0);
+                                                            acc_cols, pf_dist, w_rows_per_k, w_row0, round_a);
   return 0;
 }
 
 static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm, const uint16_t *lmap,
                           const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
                           const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
-                          int64_t ldo, int w_rows_per_k, int w_row0, cudaStream_t st) {
+                          int64_t ldo, int w_rows_per_k, int w_row0, int round_a, cudaStream_t st) {
   // TMEM: accumulator (Cout <= 128 columns, rounded to 32) + NS A slots of 64 columns = at most 256 columns, so that two
   // CTAs share an SM (one CTA's halo load, prologue and epilogue hide behind the other's stages) when shared memory allows
   // it too: three slots up to Cout = 64, two up to Cout = 128.  The weight ring takes whatever shared memory is left, up
@@ -582,7 +584,7 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
   const HaloSmem L = halo_layout(nw, Cout, hcap);
   const int64_t tiles = ceil_div(n, kTile);
   int rc;
-#define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, st
+#define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, round_a, st
   if (acc_cols <= 64) rc = launch_halo<256, 3, 2>(SCN_ARGS);
   else rc = launch_halo<256, 2, 2>(SCN_ARGS);
 #undef SCN_ARGS
@@ -636,7 +638,7 @@ int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hc
 int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm,
                             const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
                             const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
-                            const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream) {
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, int round_a, void *stream) {
   if (n <= 0) return 0;
   if (!b200scn_gather_conv_tf32_ok(Cin, Cout, lda) || (reinterpret_cast<uintptr_t>(A) & 15) ||
       (reinterpret_cast<uintptr_t>(Wkm) & 15))
@@ -652,7 +654,7 @@ int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, con
   for (int n0 = 0; n0 < Cout; n0 += width) {
     const int nc = Cout - n0 < width ? Cout - n0 : width;
     if (halo_conv_part(A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, nc,
-                       addend ? addend + n0 : nullptr, ldadd, out + n0, ldo, Cout, n0, (cudaStream_t)stream))
+                       addend ? addend + n0 : nullptr, ldadd, out + n0, ldo, Cout, n0, round_a, (cudaStream_t)stream))
       return 1;
   }
   return 0;

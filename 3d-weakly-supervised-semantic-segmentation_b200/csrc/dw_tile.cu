@@ -72,15 +72,19 @@ __device__ __forceinline__ float4 dt_lds_f4(uint32_t saddr) {
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
   return v;
 }
-__device__ __forceinline__ float dt_rna(float v) {
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-  return __uint_as_float(t);
+__device__ __forceinline__ float dt_rna(float v) {   // nearest TF32, ties away, as two full-rate integer instructions
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void dt_rna4(float4 &v) { v.x = dt_rna(v.x); v.y = dt_rna(v.y); v.z = dt_rna(v.z); v.w = dt_rna(v.w); }
 __device__ __forceinline__ void dt_named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// Diagnostic: clock64 timeline of CTA 0 (b200scn_debug_dw_timeline): per tile it, slots 16*it + {0 loader waits for the
+// buffer, 1 buffer free, 2 plan slice in, 3 copies landed, 4 tile published, 5 producer 0 sees the tile, 6 producer 0 done,
+// 7 MMA thread sees the tile, 8 MMA thread done issuing, 9 stages of the tile}.
+__device__ long long *g_dw_timeline = nullptr;
+#define DW_TL(slot) do { if (tl && it < 60) tl[16 * it + (slot)] = clock64(); } while (0)
 
 // Warp 0: MMA issuer (and TMEM owner).  Warps 1..8: tile loaders (global -> registers -> shared, one tile ahead).
 // Warps 9..16: A^T stage producers (shared -> shared), then the epilogue.
@@ -113,6 +117,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
   const int ntiles = (n_rows + kDT - 1) / kDT;
   const int my_n = ci < ntiles ? (ntiles - ci + nper - 1) / nper : 0;
   const int wps = kDtProducers / nst;   // producer warps per stage
+  long long *tl = (g_dw_timeline && blockIdx.x == 0 && lane == 0) ? g_dw_timeline : nullptr;
 
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -141,7 +146,11 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
     const int cvalid = min(32, Ca - cb * 32);     // live channels of this CTA's block of A
     for (int it = 0; it < my_n; ++it) {
       const int tile = ci + it * nper, b = it % nbuf, row0 = tile * kDT;
-      mbar_wait(tempty + b, (((uint32_t)(it / nbuf)) & 1u) ^ 1u);
+      if (lt == 0) DW_TL(0);
+      // long waits suspend (try_wait with a time hint) instead of spinning: 8 loader warps polling in a tight loop took the
+      // issue slots the MMA-issuing lane and the producers needed (measured: 1180 cycles per stage with spinning waits)
+      mbar_wait_sleep(tempty + b, (((uint32_t)(it / nbuf)) & 1u) ^ 1u, 2000);
+      if (lt == 0) DW_TL(1);
       const uint32_t g_b = base + L.g_off[b], halo_b = base + L.halo_off[b], lmap_b = base + L.lmap_off[b];
       int *sorow = reinterpret_cast<int *>(sm + L.misc_off[b]);
       int *hids = sorow + kDT;
@@ -157,6 +166,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
         for (int h = lt; h < hn; h += NL) hids[h] = __ldg(ids + h);
       }
       dt_named_bar(2, NL);
+      if (lt == 0) DW_TL(2);
       // phase 2: gradient rows of the tile (B operand image) and halo rows of A (this CTA's 32 channels): every 16-byte
       // copy of the tile is in flight at once (cp.async needs no registers), one global round trip for the whole tile
       for (int e = lt; e < kDT * cpr; e += NL) {
@@ -173,6 +183,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
       }
       cp_async_wait_all();
       dt_named_bar(2, NL);
+      if (lt == 0) DW_TL(3);
       // the G tile is consumed by the tensor core as it lies: round it to the nearest TF32 in place (the A rows are
       // rounded by the stage producers on their way through registers)
       for (int e0 = lt; e0 < kDT * cpr; e0 += 4 * NL) {
@@ -202,6 +213,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
       fence_proxy_async();   // the G tile is read by the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(tfull + b);
+      if (lt == 0) DW_TL(4);
     }
   } else if (warp > kDtLoaders) {
     // ------------------------------------------------------------------------------------------ A^T stage producers
@@ -213,7 +225,8 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
     int st = 0;
     for (int it = 0; it < my_n; ++it) {
       const int b = it % nbuf;
-      mbar_wait(tfull + b, ((uint32_t)(it / nbuf)) & 1u);
+      mbar_wait_sleep(tfull + b, ((uint32_t)(it / nbuf)) & 1u, 1000);
+      if (pw == 0) DW_TL(5);
       const uint32_t halo_b = base + L.halo_off[b];
       const int *sorow = reinterpret_cast<const int *>(sm + L.misc_off[b]);
       const uint8_t *cm = reinterpret_cast<const uint8_t *>(sorow + kDT + hcap);
@@ -231,7 +244,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
           if (!any) continue;
           if (st % nst == my_stage) {
             const int buf = my_stage;
-            mbar_wait(empty + buf, (((uint32_t)(st / nst)) & 1u) ^ 1u);
+            mbar_wait_sleep(empty + buf, (((uint32_t)(st / nst)) & 1u) ^ 1u, 200);
             const uint32_t st_base = base + L.stage_off + (uint32_t)buf * kStageBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -271,6 +284,7 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + b);   // this warp no longer reads the tile's halo / plan
+      if (pw == 0) DW_TL(6);
     }
   } else if (elect_one()) {
     // ------------------------------------------------------------------------------------------ MMA issuer
@@ -283,6 +297,8 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
     for (int it = 0; it < my_n; ++it) {
       const int b = it % nbuf;
       mbar_wait(tfull + b, ((uint32_t)(it / nbuf)) & 1u);
+      if (g_dw_timeline && blockIdx.x == 0 && it < 60) g_dw_timeline[16 * it + 7] = clock64();
+      const int st_begin = st;
       const uint8_t *cm = reinterpret_cast<const uint8_t *>(reinterpret_cast<const int *>(sm + L.misc_off[b]) + kDT + hcap);
       const uint32_t g_b = base + L.g_off[b];
       for (int g = 0; g < ng; ++g) {
@@ -309,6 +325,10 @@ dw_tile_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict
         }
       }
       mma_commit(tempty + b);   // arrives once every MMA reading this G tile has completed
+      if (g_dw_timeline && blockIdx.x == 0 && it < 60) {
+        g_dw_timeline[16 * it + 8] = clock64();
+        g_dw_timeline[16 * it + 9] = st - st_begin;
+      }
     }
     *acc_mask_s = acc_mask;
     mma_commit(done);
@@ -402,6 +422,13 @@ static DwPlan dw_plan(int64_t n, int hcap, int Ca, int Cg) {
 using namespace b200scn;
 
 extern "C" {
+
+/* diagnostic (not in the public header): later b200scn_subm_dw_tiled launches record a clock64 timeline of CTA 0 into buf
+ * (1024 int64, device); buf = NULL switches it off */
+int b200scn_debug_dw_timeline(long long *buf) {
+  SCN_CUDA(cudaMemcpyToSymbol(g_dw_timeline, &buf, sizeof(buf)));
+  return 0;
+}
 
 size_t b200scn_subm_dw_tiled_scratch_bytes(int64_t n, int hcap, int Ca, int Cg) {
   const DwPlan p = dw_plan(n, hcap, Ca, Cg);

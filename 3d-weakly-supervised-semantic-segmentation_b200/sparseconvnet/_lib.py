@@ -40,8 +40,10 @@ SIGNATURES = {
     "b200scn_gather_conv_tf32_ok": (_i32, [_i32, _i32, _i64]),
     "b200scn_gather_conv": (_i32, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
     "b200scn_morton_keys": (_i32, [_vp, _i64, _vp, _vp]),
+    "b200scn_morton_perm_scratch_bytes": (_sz, [_i64]),
+    "b200scn_morton_perm": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "b200scn_tile_plan": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "b200scn_subm_conv_tiled": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _vp]),
+    "b200scn_subm_conv_tiled": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
     "b200scn_subm_dw_tiled_scratch_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "b200scn_subm_dw_tiled": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "b200scn_prep_weight_tf32": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -32,6 +32,7 @@ class Level:
         self.pairs_ordered = None
         self._counts = None
         self.plan = None          # TilePlan of the spatially tiled convolution
+        self.batch_bits = 15      # sample-index bits sorted by the Morton ordering (InputLayer narrows it to the batch)
 
     def tile_plan(self, hcap):
         """Morton-ordered 128-row tiles + per-tile halo lists (b200scn_tile_plan), built once per level and step."""
@@ -87,14 +88,15 @@ class TilePlan:
         dev = nbr.device
         n = level.n
         st = _lib.stream_for(nbr)
-        # curve keys live in a quantised-capacity buffer padded with +inf keys, so that the sort (torch's radix sort --
-        # plumbing) and its outputs have sizes that repeat from step to step (see _lib.round_rows) and padding sorts last
-        cap = _lib.round_rows(max(n, 1))
         from . import ops as _ops
-        tok = _ops._p0("morton_sort", "morton_keys+sort", 8.0 * n + 8.0 * n + 4.0 * n, 0, 0.0, 0.0)
-        mk = torch.full((cap,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
-        check(lib.b200scn_morton_keys(ptr(level.ukeys), n, ptr(mk), st))
-        self.perm = torch.sort(mk)[1].to(torch.int32)[:n]   # keys are unique; b < 2^15 keeps them positive
+        tok = _ops._p0("morton_sort", "morton_perm (keys + radix sort)", 8.0 * n + 2 * 12.0 * n * 4 + 4.0 * n, 0, 0.0, 0.0)
+        # site ids along the Morton curve: key build + radix sort inside the library (b200scn_morton_perm); the sample
+        # index needs ceil(log2(batch)) bits, bounded here by the 15 bits the packed key reserves for it
+        nbytes = lib.b200scn_morton_perm_scratch_bytes(_lib.round_rows(max(n, 1)))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.perm = alloc_flat(max(n, 1), dev, torch.int32)[:n]
+        check(lib.b200scn_morton_perm(ptr(level.ukeys), n, level.size, level.batch_bits, ptr(self.perm), ptr(scratch), nbytes,
+                                      st))
         _ops._p1(tok)
         T = (n + 127) // 128
         self.hcap = hcap

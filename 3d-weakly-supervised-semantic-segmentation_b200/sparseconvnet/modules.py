@@ -116,7 +116,8 @@ class Sequential(torch.nn.Sequential):
                 if isinstance(branch[0], BatchNormalization) and len(branch) > 1 and input.features.requires_grad:
                     # x feeds the BatchNorm AND the skip: one function returns both, so that backward sums the two
                     # gradients inside the BatchNorm backward kernel
-                    y, input = branch[0].forward_with_alias(input, _bn_feeds_conv(branch[0], branch[1]))
+                    y = branch[0](input, feeds_conv=_bn_feeds_conv(branch[0], branch[1]), want_alias=True)   # (hooks fire)
+                    input = y.skip_alias
                     rest = list(enumerate(branch[:-1]))[1:]
                 else:
                     rest = list(enumerate(branch[:-1]))
@@ -277,7 +278,7 @@ class SubmanifoldConvolution(_ConvBase):
         """addend: optional (N, nOut) features added to the result in the kernel's epilogue (fused residual add)."""
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, self.nOut, input)
         level = input.metadata.levels[_size(input)]
-        feats = ops.SubmanifoldConvFn.apply(input.features, self._w(), level, addend)
+        feats = ops.SubmanifoldConvFn.apply(input.features, self._w(), level, addend, getattr(input, "tf32_rounded", False))
         return self._finish(input, feats, input.spatial_size, level)
 
     def input_spatial_size(self, out_size):
@@ -449,24 +450,23 @@ class BatchNormalization(Module):
                 state_dict[prefix + new] = state_dict.pop(prefix + old)
         return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
-    def forward(self, input, feeds_conv=False):
+    def forward(self, input, feeds_conv=False, want_alias=False):
         """feeds_conv: set by Sequential when the next module is a convolution -- on the TF32 path the output is then
-        written rounded to the nearest TF32 (the tensor core would truncate it when it fetches the operand)."""
+        written rounded to the nearest TF32 (the tensor core would truncate it when it fetches the operand).
+        want_alias: the result also carries `.skip_alias`, a tensor with the INPUT's features for the residual skip;
+        gradients flowing back into it are summed with the BatchNorm's own input gradient in one kernel
+        (ops.BatchNormSkipFn) instead of by a separate autograd add."""
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
         out = SparseConvNetTensor(None, input.metadata, input.spatial_size)
-        out.features = ops.BatchNormFn.apply(input.features, self.weight, self.bias, self.running_mean,
-                                             self.running_var, self.eps, self.momentum, self.training,
-                                             self.leakiness, feeds_conv)
+        args = (input.features, self.weight, self.bias, self.running_mean, self.running_var, self.eps, self.momentum,
+                self.training, self.leakiness, feeds_conv)
+        out.tf32_rounded = bool(feeds_conv) and ops.get_precision() == "tf32"   # consumers need not round again
+        if want_alias:
+            out.features, xa = ops.BatchNormSkipFn.apply(*args)
+            out.skip_alias = SparseConvNetTensor(xa, input.metadata, input.spatial_size)
+        else:
+            out.features = ops.BatchNormFn.apply(*args)
         return out
-
-    def forward_with_alias(self, input, feeds_conv=False):
-        """-> (bn(input), input'): input' carries the same features; gradients flowing back into it are summed with the
-        BatchNorm's own input gradient in one kernel (ops.BatchNormSkipFn)."""
-        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
-        y, xa = ops.BatchNormSkipFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
-                                          self.eps, self.momentum, self.training, self.leakiness, feeds_conv)
-        return (SparseConvNetTensor(y, input.metadata, input.spatial_size),
-                SparseConvNetTensor(xa, input.metadata, input.spatial_size))
 
     def input_spatial_size(self, out_size):
         return out_size

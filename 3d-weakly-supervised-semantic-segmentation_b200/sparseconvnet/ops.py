@@ -167,7 +167,7 @@ def _use_tiled(n):
     return mode == "1" or n >= _halo["min_rows"]
 
 
-def subm_conv(x, level, gw, addend=None):
+def subm_conv(x, level, gw, addend=None, round_a=True):
     """out[o] = sum_k x[nbr[o,k]] @ Wg[k] over the level's 3x3x3 neighbour map (forward, and backward-input with the
     mirrored transposed weights)."""
     x, ldx = _c(x)
@@ -184,7 +184,7 @@ def subm_conv(x, level, gw, addend=None):
               level, 8.0, 2.0 * Cin * Cout)
     check(lib.b200scn_subm_conv_tiled(ptr(x), ldx, ptr(level.nbr), ptr(plan.perm), ptr(plan.lmap), ptr(plan.halo_ids),
                                       ptr(plan.halo_n), ptr(plan.kmask), plan.hcap, level.n, ptr(w), Cin, Cout,
-                                      ptr(addend), lda, ptr(out), Cout, _lib.stream_for(x)))
+                                      ptr(addend), lda, ptr(out), Cout, 1 if round_a else 0, _lib.stream_for(x)))
     _p1(tok)
     return out
 
@@ -246,11 +246,13 @@ def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max, rules=None):
     return dw
 
 
-_dw_tiled = [True]
+_dw_tiled = [False]
 
 
 def set_tiled_dw(on):
-    """Tile-stationary weight gradient (dw_tile.cu) on levels where the tiled forward kernel runs (default on)."""
+    """Tile-stationary, bit-reproducible weight gradient (dw_tile.cu) on levels where the tiled forward kernel runs.
+    Default OFF: measured 2.5-3.3x slower than the pair-list kernel on B200 (profiles/r2_dw_tile.md) -- its stages are
+    <= 37 % dense in the reduction dimension and each stage costs a full producer -> MMA -> producer round trip."""
     _dw_tiled[0] = bool(on)
 
 
@@ -280,11 +282,11 @@ class SubmanifoldConvFn(torch.autograd.Function):
     SubmanifoldConvolution_updateOutput / _backward."""
 
     @staticmethod
-    def forward(ctx, x, w, level, addend=None):
+    def forward(ctx, x, w, level, addend=None, x_rounded=False):
         ctx.level = level
         ctx.save_for_backward(x, w)
         fwd, ctx.w_bwd = prep_both(w, True) if ctx.needs_input_grad[0] else (None, None)
-        return subm_conv(x, level, GemmWeight(w, prepared=fwd), addend=addend)
+        return subm_conv(x, level, GemmWeight(w, prepared=fwd), addend=addend, round_a=not x_rounded)
 
     @staticmethod
     def backward(ctx, g):
@@ -304,7 +306,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
                 else:
                     pin, pout, offs = level.subm_pairs()
                 dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
-        return dx, dw, None, (g if ctx.needs_input_grad[3] else None)
+        return dx, dw, None, (g if ctx.needs_input_grad[3] else None), None
 
 
 class ConvolutionFn(torch.autograd.Function):

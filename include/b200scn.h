@@ -107,13 +107,21 @@ int b200scn_gather_conv(const float *A, int64_t lda, int64_t n_in, const int32_t
  *   kmask[t]  bit k set iff offset k occurs in the tile.
  * hcap: multiple of 8 in [8,512].  lmap must be 16-byte aligned and hold ceil(n/128)*3456 entries. */
 int b200scn_morton_keys(const uint64_t *ukeys, int64_t n, uint64_t *mkeys, void *stream);
+/* the whole ordering inside the library: perm[0..n) = site ids sorted by (sample, Morton code of x,y,z) -- key build + LSD
+ * radix sort of (key, id) pairs over the significant bits only (3*ceil(log2(spatial_size)) coordinate bits, batch_bits sample
+ * bits).  scratch: b200scn_morton_perm_scratch_bytes(n) bytes, 256-byte aligned. */
+size_t b200scn_morton_perm_scratch_bytes(int64_t n);
+int b200scn_morton_perm(const uint64_t *ukeys, int64_t n, int64_t spatial_size, int batch_bits, int32_t *perm,
+                        void *scratch, size_t scratch_bytes, void *stream);
 int b200scn_tile_plan(const int32_t *nbr, const int32_t *perm, int64_t n, int hcap, uint16_t *lmap,
                       int32_t *halo_ids, int32_t *halo_n, uint32_t *kmask, void *stream);
-/* out[o,:] = sum_k A[nbr[o*27+k],:] . W[k] (+ addend[o,:]);  W K-major (27,Cout,Cin); shapes as for precision 1 above. */
+/* out[o,:] = sum_k A[nbr[o*27+k],:] . W[k] (+ addend[o,:]);  W K-major (27,Cout,Cin); shapes as for precision 1 above.
+ * round_a != 0: rows of A are rounded to the nearest TF32 on their way into tensor memory (the tensor core would truncate);
+ * 0 when the producer already wrote them rounded (b200scn_bn_forward with round_tf32). */
 int b200scn_subm_conv_tiled(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm,
                             const uint16_t *lmap, const int32_t *halo_ids, const int32_t *halo_n,
                             const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin, int Cout,
-                            const float *addend, int64_t ldadd, float *out, int64_t ldo, void *stream);
+                            const float *addend, int64_t ldadd, float *out, int64_t ldo, int round_a, void *stream);
 
 /* Tile-stationary weight gradient of the submanifold convolution (weight-gradient half of
  * SubmanifoldConvolution_backward) on the SAME plan as b200scn_subm_conv_tiled: dW (27,Ca,Cg) = sum over the rules of

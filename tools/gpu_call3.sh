@@ -1,6 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out/r2
-python tools/ncu_target.py conv dw > gpurun_out/r2/ncu_target_plain.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:"halo_conv_tc_kernel|dw_tile_kernel" --launch-skip 4 -c 4 \
-    -o gpurun_out/r2/r2_hot -f python tools/ncu_target.py conv dw > gpurun_out/r2/ncu_hot.log 2>&1
-tail -5 gpurun_out/r2/ncu_hot.log; ls -la gpurun_out/r2/
+python tools/dw_timeline.py 32 32 0 2>&1 | tee gpurun_out/r2/dw_timeline_32_0.txt
+python tools/dw_timeline.py 64 64 1 2>&1 | tee gpurun_out/r2/dw_timeline_64_1.txt
