@@ -8,7 +8,7 @@ import types
 
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library is missing)
 from ._lib import B200SCNError, launch_count, set_option
-from .metadata import Metadata, set_pyramid_hint
+from .metadata import Metadata, PackedKeys, set_pyramid_hint
 from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, ConcatTable, Convolution,
                       Deconvolution, Identity, InputLayer, JoinTable, NetworkInNetwork, OutputLayer, Sequential,
                       SparseConvNetTensor, SubmanifoldConvolution, UnPooling)

@@ -54,6 +54,10 @@ SIGNATURES = {
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200scn_unpool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
+    "b200scn_augment_scratch_bytes": (_sz, [_i64, _i32]),
+    "b200scn_augment_voxelize": (_i32, [_vp, _i64, _vp, _i32, _vp, ctypes.c_double, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _sz, _vp]),
+    "b200scn_gather_rows": (_i32, [_vp, _i64, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "b200scn_bn_forward": (_i32, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _f32, _vp, _i64, _vp, _i32, _vp]),
     "b200scn_bn_backward": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "b200scn_bn_scratch_doubles": (_sz, [_i32]),
@@ -71,6 +75,8 @@ SIGNATURES = {
     "b200scn_sparse_to_dense": (_i32, [_vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp]),
     "b200scn_sparse_to_dense_bwd": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "b200scn_p2m_ball_query": (_i32, [_i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b200scn_p2m_ball_query_scratch_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "b200scn_p2m_ball_query_bucketed": (_i32, [_i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _sz, _vp]),
     "b200scn_p2m_group_points": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200scn_p2m_group_points_grad": (_i32, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
 }

@@ -21,6 +21,23 @@ def set_pyramid_hint(stride, depth):
     _pyramid_hint[0], _pyramid_hint[1] = int(stride), int(depth)
 
 
+class PackedKeys:
+    """Level-0 coordinates already on the device in the library's packed form (b << 48 | x << 32 | y << 16 | z, int64, one per
+    point, all inside the spatial size): what b200scn_augment_voxelize produces.  `InputLayer` accepts it in place of the
+    (sum P, 3|4) LongTensor and skips the packing / range check."""
+
+    def __init__(self, keys, batch_size=None):
+        assert keys.dtype == torch.int64 and keys.dim() == 1 and keys.is_cuda
+        self.keys, self.batch_size = keys, batch_size
+
+    def size(self, dim=None):
+        return self.keys.shape[0] if dim in (0, None) else 4
+
+    @property
+    def shape(self):
+        return (self.keys.shape[0], 4)
+
+
 class Level:
     """One spatial size: its sites (keys in id order), hash table, lazily built 3^3 neighbour map and pair lists."""
 
@@ -179,13 +196,15 @@ class Metadata:
     # ------------------------------------------------------------------ InputLayer
     def build_input(self, coords, spatial_size, mode, device):
         """coords (P,3|4) int64 on any device -> level-0 grid (+ speculative strided pyramid)."""
-        if coords.dim() != 2 or coords.shape[1] not in (3, 4):
-            raise ValueError("InputLayer: coords must be (N,3) or (N,4), got %s" % (tuple(coords.shape),))
-        coords = coords.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+        packed = coords if isinstance(coords, PackedKeys) else None
+        if packed is None:
+            if coords.dim() != 2 or coords.shape[1] not in (3, 4):
+                raise ValueError("InputLayer: coords must be (N,3) or (N,4), got %s" % (tuple(coords.shape),))
+            coords = coords.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
         P = coords.shape[0]
         Pc = _lib.round_rows(max(P, 1))   # quantised capacity of every per-point / per-site buffer
         self.P, self.mode = P, mode
-        st = _lib.stream_for(coords)
+        st = _lib.stream_for(coords if packed is None else packed.keys)
         i32, i64 = torch.int32, torch.int64
         keys = torch.empty(Pc, dtype=i64, device=device)
         s_hint, depth = _pyramid_hint
@@ -197,8 +216,11 @@ class Metadata:
         hdr = torch.zeros(1 + nlev, dtype=i32, device=device)
         from . import ops as _ops
         # algorithmic bytes: 32 P coords read + 4 P ids written; the coarse levels re-hash <= P keys each
-        tok = _ops._p0("grid_build", "pack_coords+hash+scan (all levels)", 36.0 * P, 0, 0.0, 0.0)
-        check(lib.b200scn_pack_coords(ptr(coords), P, coords.shape[1], int(spatial_size), ptr(keys), ptr(hdr), st))
+        tok = _ops._p0("grid_build", "pack_coords+hash+scan (all levels)", 36.0 * P if packed is None else 12.0 * P, 0, 0.0, 0.0)
+        if packed is None:
+            check(lib.b200scn_pack_coords(ptr(coords), P, coords.shape[1], int(spatial_size), ptr(keys), ptr(hdr), st))
+        else:
+            keys[:P].copy_(packed.keys)   # (the packed point keys are reused below as scratch of the coarse levels)
         cap = lib.b200scn_hash_capacity(Pc)
         sbytes = lib.b200scn_grid_scratch_bytes(Pc)
         scratch = torch.empty(sbytes, dtype=torch.uint8, device=device)

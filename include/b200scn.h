@@ -174,6 +174,25 @@ int b200scn_unpool(const float *in, int64_t ldi, const int32_t *parent, int64_t 
 int b200scn_unpool_bwd(const float *d_out, int64_t ldd, const int32_t *child, int64_t n_coarse, int K,
                        int C, float *d_in, int64_t ldi, void *stream);
 
+/* ------------------------------------------------------------------ data path on the GPU (f2) */
+/* dataset/data.py:165-200 (trainMerge, form 0) / :266-290 (valMerge, form 1) ending in the packed keys b200scn_grid_build
+ * consumes: per scene b (points scene_start[b]..scene_start[b+1], B+1 device ints) a = xyz . mats[b] (+ pre0 + pre[b] if pre)
+ * in float64, offset from the scene's min/max and the host-drawn r1, r2 (B x 3 doubles each) exactly as the reference
+ * computes it, rows outside [0, spatial_size)^3 dropped, coordinates truncated.  Outputs (device): keys / kept_rows of the
+ * kept points in input order (capacity P), *n_kept_dev, kept_per_scene[B] (-> batch_offsets), offset_out[B x 3].
+ * scratch: b200scn_augment_scratch_bytes(P, B). */
+size_t b200scn_augment_scratch_bytes(int64_t P, int B);
+int b200scn_augment_voxelize(const float *xyz, int64_t P, const int32_t *scene_start, int B, const double *mats,
+                             double pre0, const double *pre, const double *r1, const double *r2, int form,
+                             int64_t spatial_size, uint64_t *keys, int32_t *kept_rows, int32_t *n_kept_dev,
+                             int32_t *kept_per_scene, double *offset_out, void *scratch, size_t scratch_bytes,
+                             void *stream);
+/* out[j,:] = src[rows[j],:] (+ add_per_scene[scene of rows[j],:]) for j < *n_dev (n_max if n_dev is NULL): features of the
+ * kept points, with the per-scene colour jitter of data.py:200 folded in */
+int b200scn_gather_rows(const float *src, int64_t lds, const int32_t *rows, const int32_t *n_dev, int64_t n_max, int C,
+                        const float *add_per_scene, const int32_t *scene_start, int B, float *out, int64_t ldo,
+                        void *stream);
+
 /* ------------------------------------------------------------------ BatchNormReLU (A8) */
 /* scratch: b200scn_bn_scratch_doubles(C) doubles, ZERO on entry and left zero on exit (self-cleaning: the reduction
  * kernel's last block finalises the statistics and clears the accumulators, so one persistent zero-initialised buffer per
@@ -252,6 +271,15 @@ int b200scn_sparse_to_dense_bwd(const float *d_dense, const uint64_t *ukeys, int
  * (-1 sentinel included). */
 int b200scn_p2m_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xy,
                            const float *xy, const int32_t *pointnums, int32_t *idx, void *stream);
+/* Cell-bucketed ball query with IDENTICAL results (first nsample hits in ascending point index among the first n - ptnum
+ * points, -1 sentinel): candidates are counting-sorted into cells of side `radius` over the queries' bounding box and each
+ * query merges the index-sorted lists of the <= 4 x 4 cells covering [q - r, q + r]^2 -- O(points near the query) instead of
+ * O(n) per query (production shape: 64 x 65 536 queries x 200 k points).  max_side >= (query extent / radius) + 3 cells per
+ * axis; scratch: b200scn_p2m_ball_query_scratch_bytes(b, n, m, max_side). */
+size_t b200scn_p2m_ball_query_scratch_bytes(int b, int n, int m, int max_side);
+int b200scn_p2m_ball_query_bucketed(int b, int n, int m, float radius, int nsample, const float *new_xy,
+                                    const float *xy, const int32_t *pointnums, int32_t *idx, int max_side,
+                                    void *scratch, size_t scratch_bytes, void *stream);
 /* ops/point2mask/_ext_src/src/group_points.cpp:12-36 / 38-62. out / grad_points fully written. */
 int b200scn_p2m_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                              const int32_t *idx, float *out, void *stream);

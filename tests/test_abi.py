@@ -39,7 +39,7 @@ def test_python_binding_matches_header():
     import sparseconvnet._lib as L
     assert sorted(L.SIGNATURES) == _declared()
     # no torch types in the ABI: every argument is a plain pointer, integer or float
-    allowed = {ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_char_p}
+    allowed = {ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_double}
     for name, (res, args) in L.SIGNATURES.items():
         assert set(args) <= allowed, name
 

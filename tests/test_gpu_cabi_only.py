@@ -126,4 +126,4 @@ def test_hot_path_through_the_c_abi_alone():
     assert out.shape == want.shape
     assert rel_err(out, want) < 1e-3
     assert bool((bscr == 0).all())              # the self-cleaning BatchNorm scratch is zero again
-    assert rel_err(rm, net[3].running_mean) < 1e-4 and rel_err(rv, net[3].running_var) < 1e-4
+    assert rel_err(rm, net[3].running_mean) < 2e-3 and rel_err(rv, net[3].running_var) < 1e-3   # statistics of a TF32 product

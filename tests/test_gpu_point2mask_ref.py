@@ -45,9 +45,11 @@ def test_against_reference_extension(ref_ext, b, n, res, radius, nsample, seed):
     import point2mask_ext as ext
     q, xy, ptnum = _case(b, n, res, seed)
     idx_ref = ref_ext.ball_query(q, xy, ptnum, radius, nsample)
-    idx = ext.ball_query(q, xy, ptnum, radius, nsample)
+    idx = ext.ball_query(q, xy, ptnum, radius, nsample, bucketed=False)   # shared-memory scan kernel
     assert idx.dtype == idx_ref.dtype == torch.int32 and idx.shape == idx_ref.shape
     assert torch.equal(idx, idx_ref)                                    # bit-exact incl. the -1 sentinel
+    idx_b = ext.ball_query(q, xy, ptnum, radius, nsample, bucketed=True)  # cell-bucketed kernel: identical
+    assert torch.equal(idx_b, idx_ref)
     assert int((idx_ref[0] >= 0).sum()) == 0                            # n - ptnum == 0: nothing scanned
     torch.manual_seed(seed)
     feats = torch.randn(b, 2, n, device="cuda")
@@ -69,3 +71,33 @@ def test_oracle_restatement_matches_reference(ref_ext):
     idx_ref = ref_ext.ball_query(q, xy, ptnum, 2.0, 5).cpu().numpy()
     idx_o = ref.ball_query(2.0, 5, xy.cpu().numpy(), q.cpu().numpy(), ptnum.cpu().numpy())
     assert np.array_equal(idx_o, idx_ref)
+
+
+def test_production_shape_bucketed(ref_ext):
+    """ops/pseudo_dataset_generator/configs.py:11-12 + preprocess_mask.py:20,31-32: blur radius 1, 20 samples, 256 x 256
+    pixel-centre queries, ~200 k points per instance, padded instances; 8 of the 64 instances of a production batch (the
+    reference extension scans O(m n) per instance, so the full batch would take it minutes).  Bit-exact vs the reference,
+    and the speed-up is printed for profiles/."""
+    import time
+    import point2mask_ext as ext
+    b, n, res = 8, 200000, 256
+    q, xy, ptnum = _case(b, n, res, 11)
+    ptnum[:] = torch.randint(0, n // 3, (b,), dtype=torch.int32)
+    ptnum[0] = 0
+    ptnum = ptnum.cuda()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        return out, time.perf_counter() - t0
+
+    idx_ref, t_ref = timed(lambda: ref_ext.ball_query(q, xy, ptnum, 1.0, 20))
+    idx_scan, t_scan = timed(lambda: ext.ball_query(q, xy, ptnum, 1.0, 20, bucketed=False))
+    idx_b, t_b = timed(lambda: ext.ball_query(q, xy, ptnum, 1.0, 20, bucketed=True))
+    assert torch.equal(idx_scan, idx_ref) and torch.equal(idx_b, idx_ref)
+    pts = float(b) * res * res
+    print("point2mask ball_query B=%d m=%d n=%d r=1 nsample=20: reference ext %.1f ms, scan kernel %.1f ms, bucketed %.2f ms "
+          "(%.0fx vs reference; %.1f M queries/s)" % (b, res * res, n, 1e3 * t_ref, 1e3 * t_scan, 1e3 * t_b, t_ref / t_b, pts / t_b / 1e6))
