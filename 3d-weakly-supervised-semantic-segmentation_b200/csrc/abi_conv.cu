@@ -104,6 +104,7 @@ extern "C" int b200scn_set_option(const char *name, int value) {
   else if (!strcmp(name, "tc_nsplit")) g_opt.tc_nsplit = value;
   else if (!strcmp(name, "dw_chunk")) g_opt.dw_chunk = value >= 512 ? value : 512;
   else if (!strcmp(name, "halo_pf")) g_opt.halo_pf = value;
+  else if (!strcmp(name, "halo_dbg")) g_opt.halo_dbg = value;
   else if (!strcmp(name, "halo_one_cta")) g_opt.halo_one_cta = value;
   else return set_error("set_option: unknown option '%s'", name);
   return 0;

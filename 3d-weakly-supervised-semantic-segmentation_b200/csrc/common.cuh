@@ -34,6 +34,7 @@ struct Options {
   int tc_nsplit = 0;     // 0 auto, >0: split the offsets of the gather kernel over this many CTAs
   int dw_chunk = 4096;   // pairs per CTA of the pair-list weight-gradient kernel
   int halo_pf = -1;      // L2 prefetch distance of the tiled kernel in tiles (-1 auto, 0 off)
+  int halo_dbg = 0;      // knockout experiments of the tiled kernel (WRONG RESULTS): 1 no A build, 2 no MMA, 4 no halo reads, 8 no TMEM stores
   int halo_one_cta = 0;  // 1: force one CTA per SM in the tiled kernel
 };
 extern Options g_opt;

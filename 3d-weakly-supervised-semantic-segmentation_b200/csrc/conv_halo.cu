@@ -208,7 +208,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
                     int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int pf_dist, int w_rows_per_k, int w_row0,
-                    int round_a) {
+                    int round_a, int dbg) {
   constexpr int NPW = 4 * NS;
   constexpr int NTHREADS = 32 * (NPW + 2);
   extern __shared__ uint8_t smem_raw[];
@@ -257,7 +257,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         const int h = (tid >> 3) + 4 * NPW * j;
         if (h < hn) {
           if (c == 0) shids[h] = hid[j];
-          if (c * 4 < Cin)
+          if (c * 4 < Cin && !(dbg & 16))
             cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)hid[j] * lda, 16u);
         }
       }
@@ -297,7 +297,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   // chunk of different rows spread over the banks
   auto load_halo = [&](int kb) {
     const int c = tid & 7;
-    if (c * 4 < min(32, Cin - kb * 32)) {
+    if (c * 4 < min(32, Cin - kb * 32) && !(dbg & 16)) {
       const float *acol = A + kb * 32 + c * 4;
       for (int h = tid >> 3; h < hn; h += 4 * NPW)
         cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)shids[h] * lda, 16u);
@@ -339,7 +339,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       const int v2_end = (kb + 1) * nk2;
       // Software pipeline: the first 16 channels of the warp's NEXT visit are read from the halo into registers while the
       // tensor pipe still owns the slot; the rest follows right after "slot free", under the first TMEM store.
-      float4 p0, p1, p2, p3;
+      float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
       uint32_t slot0 = kAbsent, slot1 = kAbsent;
       int k0 = 0, k1 = 0;
       bool any = false;
@@ -347,6 +347,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       // capacity read it too and are then fetched through the global neighbour map under a warp-uniform test (rare).
       bool ovf = false;
       auto load_half = [&](uint32_t slot, int k, int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
+        if (dbg & 5) return;   // knockout experiment (b200scn_set_option "halo_dbg"): no halo reads
         const uint32_t rowi = slot < kOverflow ? slot : (uint32_t)hcap;
         const uint32_t rb = halo_base + rowi * 128;
         a0 = lds_f4(rb + (((rowi + 4 * hf + 0) & 7u) << 4));
@@ -391,22 +392,22 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         mbar_wait(empty + g, ((uint32_t)(v2 / NS) & 1u) ^ 1u);
         tc_fence_after();
         if (q == 0 && v2 / NS < 128) SCN_TL(64 + g * 256 + 2 * (v2 / NS));
-        if (any || dirty) {
+        if ((any || dirty) && !(dbg & 1)) {
           // (measured, no gain: a second register set so that the next half-row's reads fly under the previous TMEM store)
-          float4 u0, u1, u2, u3;
+          float4 u0 = p0, u1 = p0, u2 = p0, u3 = p0;
           if (cvalid > 16) {
             load_half(slot0, k0, 1, u0, u1, u2, u3);
-            tmem_st16(a_tm, p0, p1, p2, p3);
-            tmem_st16(a_tm + 16, u0, u1, u2, u3);
+            if (!(dbg & 8)) tmem_st16(a_tm, p0, p1, p2, p3);
+            if (!(dbg & 8)) tmem_st16(a_tm + 16, u0, u1, u2, u3);
           } else {
-            tmem_st16(a_tm, p0, p1, p2, p3);
+            if (!(dbg & 8)) tmem_st16(a_tm, p0, p1, p2, p3);
           }
           if (two) {
             load_half(slot1, k1, 0, u0, u1, u2, u3);
-            tmem_st16(a_tm + 32, u0, u1, u2, u3);
+            if (!(dbg & 8)) tmem_st16(a_tm + 32, u0, u1, u2, u3);
             if (cvalid > 16) {
               load_half(slot1, k1, 1, u0, u1, u2, u3);
-              tmem_st16(a_tm + 48, u0, u1, u2, u3);
+              if (!(dbg & 8)) tmem_st16(a_tm + 48, u0, u1, u2, u3);
             }
           }
           if (q == 0 && v2 / NS < 128) SCN_TL(2200 + g * 512 + 4 * (v2 / NS));
@@ -453,7 +454,8 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     int ws = 0, s = 0;
     uint32_t b_lo = b_lo0, ph = 0, accf = 0;
     auto stage = [&](uint32_t a_tm, int nj) {
-      if (nj == 4) {
+      if (dbg & 2) {
+      } else if (nj == 4) {
         mma_tf32_ts(tmem, a_tm, desc_hi | (uint64_t)b_lo, idesc, accf);
         mma_tf32_ts(tmem, a_tm + 8, desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
         mma_tf32_ts(tmem, a_tm + 16, desc_hi | (uint64_t)(b_lo + 4), idesc, 1u);
@@ -508,7 +510,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      if (row >= 0) {
+      if (row >= 0 && !(dbg & 32)) {
         if (addend) {
           const float *ad = addend + (int64_t)row * ldadd + c0;
 #pragma unroll
@@ -550,7 +552,7 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
   const int pf_dist = g_opt.halo_pf >= 0 ? g_opt.halo_pf : kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
   kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
                                                             (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,
-                                                            acc_cols, pf_dist, w_rows_per_k, w_row0, round_a);
+                                                            acc_cols, pf_dist, w_rows_per_k, w_row0, round_a, g_opt.halo_dbg);
   return 0;
 }
 

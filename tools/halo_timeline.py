@@ -6,6 +6,7 @@ import sparseconvnet as scn
 from sparseconvnet import ops, _lib
 from b200scn_synth import make_batch
 cin, cout, lvl = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+dbg = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 scn.set_precision("tf32")
 coords, feats, _ = make_batch(list(range(5)), 50)
 x = scn.InputLayer(3, 4096, mode=4)([coords, feats.cuda()])
@@ -15,6 +16,7 @@ level = md.levels[size]
 conv = scn.SubmanifoldConvolution(3, cin, cout, 3, False).cuda()
 f = torch.randn(level.n, cin, device='cuda')
 gw = ops.GemmWeight(conv.weight.view(27, cin, cout))
+scn.set_option("halo_dbg", dbg)
 for _ in range(3): ops.subm_conv(f, level, gw)
 buf = torch.zeros(4096, dtype=torch.int64, device='cuda')
 tile = (level.n // 128) // 2
@@ -24,7 +26,7 @@ ops.subm_conv(f, level, gw); torch.cuda.synchronize()
 fn(None, -1)
 t = buf.cpu().numpy(); t0 = t[0]
 def r(i): return int(t[i] - t0) if t[i] else None
-print("level", lvl, "n", level.n, "cin", cin, "cout", cout, "tile", tile)
+print("dbg", dbg, "level", lvl, "n", level.n, "cin", cin, "cout", cout, "tile", tile)
 print("prologue done", r(1), " accum seen", r(2), " epilogue done", r(3))
 for kb in range((cin + 31) // 32): print("halo kb", kb, "start", r(32 + 2 * kb), "done", r(33 + 2 * kb))
 for g in range(4):
