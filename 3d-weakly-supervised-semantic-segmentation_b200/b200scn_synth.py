@@ -86,14 +86,54 @@ def build_encoder(scn, kind, m, block_reps, residual_blocks, full_scale=4096, di
                                       downsample=[2, 2]),
             scn.BatchNormReLU(depth * (depth + 1) * m // 2),
             scn.OutputLayer(dimension))
+    if kind == "SparseConvFCNetDirectUpPool":   # models/SparseConvNet.py:107-158 (embed_length 256)
+        nPlanes, ds = [m, 64, 128, 192, 256], [2, 2]
+
+        def block(seq, a, b):
+            if residual_blocks:
+                seq.add(scn.ConcatTable()
+                        .add(scn.Identity() if a == b else scn.NetworkInNetwork(a, b, False))
+                        .add(scn.Sequential()
+                             .add(scn.BatchNormReLU(a))
+                             .add(scn.SubmanifoldConvolution(dimension, a, b, 3, False))
+                             .add(scn.BatchNormReLU(b))
+                             .add(scn.SubmanifoldConvolution(dimension, b, b, 3, False)))).add(scn.AddTable())
+            else:
+                seq.add(scn.Sequential()
+                        .add(scn.BatchNormReLU(a))
+                        .add(scn.SubmanifoldConvolution(dimension, a, b, 3, False)))
+
+        def U(planes):
+            seq = scn.Sequential()
+            for _ in range(block_reps):
+                block(seq, planes[0], planes[0])
+            if len(planes) > 1:
+                seq.add(scn.Sequential()
+                        .add(scn.BatchNormReLU(planes[0]))
+                        .add(scn.Convolution(dimension, planes[0], planes[1], ds[0], ds[1], False))
+                        .add(U(planes[1:]))
+                        .add(scn.UnPooling(dimension, ds[0], ds[1])))
+            return seq
+        return scn.Sequential(
+            scn.InputLayer(dimension, full_scale, mode=4),
+            scn.SubmanifoldConvolution(dimension, 3, m, 3, False),
+            U(nPlanes),
+            scn.BatchNormReLU(nPlanes[-1]),
+            scn.OutputLayer(dimension))
     raise ValueError(kind)
 
+
+# embed width the heads are built with (models/SparseConvNet.py:57,73,107: `embed_length` of the registry entries)
+EMBED_WIDTH = {"SparseConvUNet": lambda m: m, "SparseConvFCNet": lambda m: 28 * m, "SparseConvFCNetDirectUpPool": lambda m: 256}
 
 # BASELINE.json configs -> (encoder kind, m, block_reps, residual, scale, batch)
 CONFIGS = {
     "cfg1_unet_m16_r1_s20_b1": ("SparseConvUNet", 16, 1, False, 20, 1),
     "cfg2_fcnet_m16_r1_s20_b8": ("SparseConvFCNet", 16, 1, False, 20, 8),
     "cfg3_unet_m32_r2_res_s50_b5": ("SparseConvUNet", 32, 2, True, 50, 5),
+    # config/3DUNetWithText_scannet_subcloud_uppool_4gpu.yaml: global batch 30 over 4 GPUs -> 8 scenes per GPU (7.5 rounded up),
+    # model MultiLabel = encoder + scene pooling + Linear(256, 20) + multilabel soft margin loss (bench.py uses the fused head)
+    "cfg4_uppool_m16_r2_res_s50_b8_head": ("SparseConvFCNetDirectUpPool", 16, 2, True, 50, 8),
     "cfg5_fcnet_m16_r2_res_s100_b6": ("SparseConvFCNet", 16, 2, True, 100, 6),
 }
 

@@ -141,6 +141,12 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ float4 lds_f4_if(uint32_t saddr, bool p) {   // lanes with !p issue no shared-memory access
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "r"(saddr), "r"((int)p));
+  return v;
+}
 // 32 lanes x 16 consecutive 32-bit columns, registers -> TMEM (lane t of the warp writes TMEM lane base + t)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const float4 &b, const float4 &c, const float4 &d) {
   asm volatile(
@@ -350,10 +356,18 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
         if (dbg & 5) return;   // knockout experiment (b200scn_set_option "halo_dbg"): no halo reads
         const uint32_t rowi = slot < kOverflow ? slot : (uint32_t)hcap;
         const uint32_t rb = halo_base + rowi * 128;
+        if (dbg & 128) {   // experiment: absent lanes issue no shared-memory access
+          const bool pr = slot < kOverflow;
+          a0 = lds_f4_if(rb + (((rowi + 4 * hf + 0) & 7u) << 4), pr);
+          a1 = lds_f4_if(rb + (((rowi + 4 * hf + 1) & 7u) << 4), pr);
+          a2 = lds_f4_if(rb + (((rowi + 4 * hf + 2) & 7u) << 4), pr);
+          a3 = lds_f4_if(rb + (((rowi + 4 * hf + 3) & 7u) << 4), pr);
+        } else {
         a0 = lds_f4(rb + (((rowi + 4 * hf + 0) & 7u) << 4));
         a1 = lds_f4(rb + (((rowi + 4 * hf + 1) & 7u) << 4));
         a2 = lds_f4(rb + (((rowi + 4 * hf + 2) & 7u) << 4));
         a3 = lds_f4(rb + (((rowi + 4 * hf + 3) & 7u) << 4));
+        }
         if (ovf && slot == kOverflow) {
           const int idx = __ldg(nbr + (int64_t)sorow[r] * 27 + k);
           const float *src = A + (int64_t)idx * lda + (kb * 32 + hf * 16);
@@ -435,7 +449,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
       uint32_t ph = 0;
       for (int it = 0; it < T; ++it) {
         if ((s & 1) == 0) mbar_wait(wempty + (s >> 1), ph ^ 1u);   // pair (s, s+1) consumed by the tensor pipe
-        mbar_arrive_expect_tx(wfull + s, b_bytes);
+        mbar_arrive_expect_tx(wfull + s, (dbg & 64) ? b_bytes >> 1 : b_bytes);   // (64: experiment, half the W bytes)
         tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, klist[ki] * w_rows_per_k + w_row0, wfull + s);
         if (++ki == nk) { ki = 0; ++kb; }
         if (++s == nw) { s = 0; ph ^= 1u; }
@@ -548,7 +562,7 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
   }
   const uint32_t idesc = make_idesc_tf32(128, Cout, 0, 0);
   alignas(64) CUtensorMap tmW;   // weight slice box: Cout rows x 32 channels of the (27*Cout_total, Cin) K-major stack
-  if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, Cout)) return 1;
+  if (make_weight_tmap(&tmW, Wkm, (int64_t)27 * w_rows_per_k, Cin, Cin, (g_opt.halo_dbg & 64) ? Cout / 2 : Cout)) return 1;
   const int pf_dist = g_opt.halo_pf >= 0 ? g_opt.halo_pf : kNumSMs * MINB;   // tiles resident at once = how far ahead the next wave is
   kern<<<(unsigned)tiles, 32 * (4 * NS + 2), L.total, st>>>(tmW, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap,
                                                             (int)n, Cin, Cout, addend, ldadd, out, ldo, idesc, L, nw,

@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200scn_output_features_bwd_csr": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "b200scn_scene_mean": (_i32, [_vp, _i64, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "b200scn_scene_mean_bwd": (_i32, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "b200scn_head_multilabel": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "b200scn_head_multilabel_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "b200scn_maxpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "b200scn_maxpool_bwd": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200scn_sparse_to_dense": (_i32, [_vp, _i64, _vp, _i64, _i32, _i64, _vp, _vp]),

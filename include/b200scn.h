@@ -252,6 +252,18 @@ int b200scn_scene_mean(const float *feats, int64_t ldf, const uint64_t *ukeys, c
 int b200scn_scene_mean_bwd(const float *g, const uint64_t *ukeys, const int32_t *count, int mode, const float *npts,
                            int64_t n, int C, float *d_feats, int64_t ldd, void *stream);
 
+/* Scene-level head fused after the pooling (f1: nn.Linear(embed, NUM_CLASSES), models/MultiLabelContrastive.py:59,66;
+ * F.multilabel_soft_margin_loss, utils/loss.py:21-30).  logits[B,NC] = pooled[B,C] W[NC,C]^T + bias; when labels[B,NC] is
+ * given, *loss = mean_b mean_c -(y log sigmoid(x) + (1-y) log sigmoid(-x)), summed in a fixed order (bit-reproducible).
+ * scratch: B + 1 floats, zeroed ONCE by the caller (the kernel leaves its completion counter at zero).
+ * Backward: dl = d_logits (optional) + *d_loss (sigmoid(x) - y) / (B NC) (when labels and d_loss are given);
+ * d_pooled = dl W, d_W = dl^T pooled, d_b = column sums of dl (d_b may be NULL). */
+int b200scn_head_multilabel(const float *pooled, const float *W, const float *bias, const float *labels, int B, int C,
+                            int NC, float *logits, float *loss, float *scratch, void *stream);
+int b200scn_head_multilabel_bwd(const float *pooled, const float *W, const float *labels, const float *logits,
+                                const float *d_loss, const float *d_logits, int B, int C, int NC, float *d_pooled,
+                                float *d_W, float *d_b, void *stream);
+
 /* scn.MaxPooling with size == stride (MaxPooling_updateOutput / _updateGradInput; models/projector/components.py:78-100):
  * out[j,:] = max(0, max over children of in[child,:]) -- upstream zero-initialises the output; the gradient goes to every
  * child that equals the pooled value. */

@@ -17,7 +17,8 @@ if len(sys.argv) > 3:
     a = [int(v) for v in sys.argv[1:]]
     shapes = [tuple(a[i:i + 3]) for i in range(0, len(a), 3)]
 CASES = [("full", 0), ("no A build", 1), ("no MMA", 2), ("no A build, no MMA", 3), ("no halo LDS", 4), ("no TMEM st", 8),
-         ("no global halo copy", 16), ("no output store", 32), ("no build/MMA/copy/store", 1 | 2 | 16 | 32)]
+         ("no global halo copy", 16), ("no output store", 32), ("no build/MMA/copy/store", 1 | 2 | 16 | 32), ("half W bytes", 64), ("half W, no build/MMA/copy/store", 64 | 1 | 2 | 16 | 32),
+         ("predicated LDS", 128), ("one CTA/SM", -1), ("one CTA/SM skeleton", -(1 | 2 | 16 | 32))]
 for cin, cout, lvl in shapes:
     level = md.levels[4096 >> lvl]
     f = torch.randn(level.n, cin, device='cuda')
@@ -25,7 +26,8 @@ for cin, cout, lvl in shapes:
     gw = ops.GemmWeight(w)
     print("== level %d  n %d  %d -> %d  tiles %d" % (lvl, level.n, cin, cout, (level.n + 127) // 128))
     for name, dbg in CASES:
-        scn.set_option("halo_dbg", dbg)
+        scn.set_option("halo_one_cta", 1 if dbg < 0 else 0)
+        scn.set_option("halo_dbg", 0 if dbg == -1 else abs(dbg))
         for _ in range(3):
             ops.subm_conv(f, level, gw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,3 +40,4 @@ for cin, cout, lvl in shapes:
         cyc = us * 1e-6 * 1.965e9 * 148 / ((level.n + 127) // 128)
         print("  %-28s %8.1f us   %7.0f SM-cycles/tile" % (name, us, cyc))
     scn.set_option("halo_dbg", 0)
+    scn.set_option("halo_one_cta", 0)
