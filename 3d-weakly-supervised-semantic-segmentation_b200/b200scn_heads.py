@@ -38,7 +38,6 @@ class MultiLabelHeadFn(torch.autograd.Function):
                                           ptr(scratch), _lib.stream_for(pooled)))
         ctx.save_for_backward(pooled, weight, labels, logits)
         ctx.has_bias = bias is not None
-        ctx.mark_non_differentiable()
         return logits, loss
 
     @staticmethod
@@ -86,6 +85,12 @@ class MultiLabelHead(nn.Module):
     def _get(batch, name):
         return batch[name] if isinstance(batch, dict) else getattr(batch, name)
 
+    def head_loss(self, y, batch_size, labels=None):
+        """Trunk output (level-0 SparseConvNetTensor) -> (global_logits, loss | None): pooling + Linear (+ loss)."""
+        pooled = self.pool(y, batch_size)
+        logits, loss = MultiLabelHeadFn.apply(pooled, self.linear.weight, self.linear.bias, labels)
+        return logits, (loss if labels is not None else None)
+
     def forward(self, x, istrain=False, labels=None):
         if istrain:
             x = x[0]
@@ -96,7 +101,4 @@ class MultiLabelHead(nn.Module):
             y = mod(y)
         if not istrain:
             return self.linear(out_layer(y))
-        B = len(self._get(x, "batch_offsets")) - 1
-        pooled = self.pool(y, B)
-        logits, loss = MultiLabelHeadFn.apply(pooled, self.linear.weight, self.linear.bias, labels)
-        return logits, (loss if labels is not None else None)
+        return self.head_loss(y, len(self._get(x, "batch_offsets")) - 1, labels)

@@ -132,6 +132,10 @@ tile_plan_kernel(const int32_t *__restrict__ nbr, const int32_t *__restrict__ pe
 // tf32 element); only the small W slice is a shared-memory operand, and one elected lane runs the whole issue loop.
 constexpr int kHaloMaxSlots = 4;   // A slots in TMEM (64 columns = two stages of 32 channels each)
 constexpr int kHaloMaxW = 16;    // weight-ring slots
+// Halo rows are stored with a pitch of 144 bytes (128 + 16): chunk c of halo row h lies at h * 144 + 16 c, i.e. in bank group
+// (h + c) mod 8 -- lanes that read the same chunk of rows that differ mod 8 never collide -- and every chunk address is the
+// row base plus a compile-time constant, so a builder's 16 row reads per visit need no address arithmetic at all.
+constexpr uint32_t kHaloPitch = 144;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -141,10 +145,15 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ float4 lds_f4_if(uint32_t saddr, bool p) {   // lanes with !p issue no shared-memory access
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
-               : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w) : "r"(saddr), "r"((int)p));
+template <int OFF>
+__device__ __forceinline__ float4 lds_f4_at(uint32_t saddr) {   // [saddr + OFF], OFF folded into the instruction
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4 + %5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
   return v;
 }
 // 32 lanes x 16 consecutive 32-bit columns, registers -> TMEM (lane t of the warp writes TMEM lane base + t)
@@ -157,10 +166,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 &a, const
 }
 // fp32 -> nearest TF32 (ties away), in place.  tcgen05.mma kind::tf32 TRUNCATES its operands to a 10-bit mantissa: a
 // one-sided error of up to 2^-10 whose mean (~3.5e-4 relative) does not average out over the reduction -- measured as a
-// coherent ~5e-4 per truncated operand in the per-op parity tests.  Rounding here makes the error zero-mean.
+// coherent ~5e-4 per truncated operand in the per-op parity tests.  Rounding makes the error zero-mean.
 // Done with two full-rate integer instructions (add half an ulp of the 10-bit mantissa to the magnitude, clear the low 13
-// bits: exactly cvt.rna.tf32.f32 for finite values) -- the conversion instruction itself issues at 16 lanes/clk/SM and
-// 32 of them per row and stage would saturate that pipe.
+// bits: exactly cvt.rna.tf32.f32 for finite values).  It is applied ONCE PER HALO ROW as the row lands in shared memory
+// (each thread rounds the chunks it copied itself), not per (row, offset) reference in the builders: a tile references
+// every halo row ~5-7 times and the builders' instruction issue is what bounds the kernel.
 __device__ __forceinline__ float rna1(float v) {
   return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
@@ -185,7 +195,7 @@ static HaloSmem halo_layout(int nw, int Cout, int hcap) {
   HaloSmem L;
   L.b_off = 0;
   L.halo_off = L.b_off + (uint32_t)nw * Cout * 128;
-  L.lmap_off = L.halo_off + ((uint32_t)hcap + 1) * 128;   // + one all-zero row that absent neighbours read
+  L.lmap_off = L.halo_off + ((uint32_t)hcap + 1) * kHaloPitch;   // + one all-zero row that absent neighbours read
   L.orow_off = L.lmap_off + ((kTileMap * 2 + 15) & ~15);
   L.hids_off = L.orow_off + kTile * 4;
   L.klist_off = L.hids_off + (((uint32_t)hcap * 4 + 15) & ~15u);
@@ -194,19 +204,22 @@ static HaloSmem halo_layout(int nw, int Cout, int hcap) {
   return L;
 }
 
-// Diagnostic: clock64 timeline of ONE CTA (b200scn_debug_timeline).  Slots: [0] start, [1] prologue done, [2] accumulator
-// seen by the epilogue, [3] epilogue done; builder warp of stage g, quarter 0: 64 + g*256 + 2*use + {0: slot free (= the
-// MMAs of the slot's previous use have completed), 1: built}; halo load of channel block kb: 32 + 2*kb + {0,1}.
+// Diagnostic (DBG instances only): clock64 timeline of ONE CTA (b200scn_debug_timeline).  Slots: [0] start, [1] prologue
+// done, [2] accumulator seen by the epilogue, [3] epilogue done; builder warp of slot g, quarter 0: 64 + g*256 + 2*use +
+// {0: slot free (= the MMAs of the slot's previous use have completed), 1: built}; halo load of channel block kb: 32 + 2*kb + {0,1}.
 __device__ long long *g_timeline = nullptr;
 __device__ int g_timeline_tile = -1;
-#define SCN_TL(slot) do { if (tl) tl[slot] = clock64(); } while (0)
+#define SCN_TL(slot) do { if (DBG && tl) tl[slot] = clock64(); } while (0)
 
 // NT: TMEM columns allocated (power of two >= acc_cols + 64 NS): accumulator in columns [0, Cout), A slot s in columns
 // [acc_cols + 64 s, + 64).  A slot holds TWO stages (two kernel offsets x 32 channels, 8 tcgen05.mma): every barrier
 // round trip -- builder <-> MMA thread <-> tensor pipe -- costs a few hundred cycles of dependent instructions on the
 // single issuing thread whatever the amount of work, so it is paid once per 8 MMAs.  4 NS builder warps
 // (warp = 4 * slot + TMEM lane quarter).  MINB: CTAs per SM the register budget is sized for.
-template <uint32_t NT, int NS, int MINB>
+// DBG: instance with the knockout switches (b200scn_set_option "halo_dbg") and the timeline probes compiled in; the
+// production instance has neither -- the builders' inner loop is bound by instruction issue (ncu: the kernel issues on
+// ~50 % of all cycles while no memory or tensor pipe is above 40 %), so every instruction in it counts.
+template <uint32_t NT, int NS, int MINB, bool DBG>
 __global__ void __launch_bounds__(32 * (4 * NS + 2), MINB)
 halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__restrict__ A, int64_t lda,
                     const int32_t *__restrict__ nbr, const int32_t *__restrict__ perm,
@@ -214,16 +227,16 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
                     const int32_t *__restrict__ halo_n, const uint32_t *__restrict__ kmask, int hcap, int n_rows,
                     int Cin, int Cout, const float *__restrict__ addend, int64_t ldadd, float *__restrict__ out,
                     int64_t ldo, uint32_t idesc, HaloSmem L, int nw, int acc_cols, int pf_dist, int w_rows_per_k, int w_row0,
-                    int round_a, int dbg) {
+                    int round_a, int dbg_arg) {
   constexpr int NPW = 4 * NS;
   constexpr int NTHREADS = 32 * (NPW + 2);
+  const int dbg = DBG ? dbg_arg : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *sm = smem_raw + (base - raw);
   const uint32_t b_bytes = (uint32_t)Cout * 128;
   const uint32_t b_base = base + L.b_off, halo_base = base + L.halo_off;
-  const uint16_t *slmap = reinterpret_cast<const uint16_t *>(sm + L.lmap_off);
   int *sorow = reinterpret_cast<int *>(sm + L.orow_off);
   int *shids = reinterpret_cast<int *>(sm + L.hids_off);
   int *klist = reinterpret_cast<int *>(sm + L.klist_off);
@@ -238,8 +251,24 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, row0 = tile * kTile;
   const int hn = __ldg(halo_n + tile);
-  long long *tl = (g_timeline && g_timeline_tile == tile && lane == 0) ? g_timeline : nullptr;
+  long long *tl = nullptr;
+  if (DBG) tl = (g_timeline && g_timeline_tile == tile && lane == 0) ? g_timeline : nullptr;
   if (tid == 0) SCN_TL(0);
+
+  // The chunks of the halo this thread copies: chunk c = tid & 7 of rows (tid >> 3) + 4 NPW j.  After its own
+  // cp.async.wait_all a thread may read back what it copied, so the TF32 rounding of the rows (round_a) is done by the
+  // copying thread, in place, before the barrier that publishes the halo.
+  const int hc = tid & 7, hr0 = tid >> 3;
+  auto round_own_chunks = [&](int cvalid) {
+    if (round_a && hc * 4 < cvalid && !(DBG && (dbg & 16))) {
+      for (int h = hr0; h < hn; h += 4 * NPW) {
+        const uint32_t a = halo_base + (uint32_t)h * kHaloPitch + (uint32_t)hc * 16;
+        float4 v = lds_f4(a);
+        rna4(v);
+        sts_f4(a, v);
+      }
+    }
+  };
 
   // ---- prologue: the tile's plan slice -> shared memory.  Every builder thread fetches the halo row ids it copies (rows
   // tid/8 + 4*NPW*j) in the same global round trip as halo_n and issues the first channel block's halo copies straight
@@ -250,26 +279,25 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     for (int e = tid; e < kTileMap * 2 / 16; e += NTHREADS) cp_async16(base + L.lmap_off + e * 16, src + e * 8, 16u);
     if (warp < NPW) {
       const int32_t *ids = halo_ids + (int64_t)tile * hcap;
-      const int c = tid & 7;
       int hid[kHidSlots];
 #pragma unroll
       for (int j = 0; j < kHidSlots; ++j) {
-        const int h = (tid >> 3) + 4 * NPW * j;
+        const int h = hr0 + 4 * NPW * j;
         hid[j] = h < hcap ? __ldg(ids + h) : 0;   // entries at and beyond halo_n are never dereferenced
       }
-      const float *acol = A + c * 4;
+      const float *acol = A + hc * 4;
 #pragma unroll
       for (int j = 0; j < kHidSlots; ++j) {
-        const int h = (tid >> 3) + 4 * NPW * j;
+        const int h = hr0 + 4 * NPW * j;
         if (h < hn) {
-          if (c == 0) shids[h] = hid[j];
-          if (c * 4 < Cin && !(dbg & 16))
-            cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)hid[j] * lda, 16u);
+          if (hc == 0) shids[h] = hid[j];
+          if (hc * 4 < Cin && !(DBG && (dbg & 16)))
+            cp_async16(halo_base + (uint32_t)h * kHaloPitch + (uint32_t)hc * 16, acol + (int64_t)hid[j] * lda, 16u);
         }
       }
     }
     if (tid < kTile) sorow[tid] = row0 + tid < n_rows ? __ldg(perm + row0 + tid) : -1;
-    if (tid < 8) sts_f4(halo_base + (uint32_t)hcap * 128 + tid * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+    if (tid < 8) sts_f4(halo_base + (uint32_t)hcap * kHaloPitch + tid * 16, make_float4(0.f, 0.f, 0.f, 0.f));
     if (tid == 0) {
       const uint32_t km = __ldg(kmask + tile);
       int n = 0;
@@ -299,17 +327,15 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     else if (tid < kTileMap * 2 / 128 + hcap * 4 / 128) prefetch_l2(pi + (tid - kTileMap * 2 / 128) * 128);
     else if (tid < kTileMap * 2 / 128 + hcap * 4 / 128 + 4) prefetch_l2(perm + (int64_t)pf_tile * kTile + (tid - kTileMap * 2 / 128 - hcap * 4 / 128) * 32);
   }
-  // halo of channel block kb: chunk c of halo row h is stored at position (c + h) & 7, so that lanes reading the same
-  // chunk of different rows spread over the banks
   auto load_halo = [&](int kb) {
-    const int c = tid & 7;
-    if (c * 4 < min(32, Cin - kb * 32) && !(dbg & 16)) {
-      const float *acol = A + kb * 32 + c * 4;
-      for (int h = tid >> 3; h < hn; h += 4 * NPW)
-        cp_async16(halo_base + (uint32_t)h * 128 + (((uint32_t)(c + h) & 7u) << 4), acol + (int64_t)shids[h] * lda, 16u);
+    if (hc * 4 < min(32, Cin - kb * 32) && !(DBG && (dbg & 16))) {
+      const float *acol = A + kb * 32 + hc * 4;
+      for (int h = hr0; h < hn; h += 4 * NPW)
+        cp_async16(halo_base + (uint32_t)h * kHaloPitch + (uint32_t)hc * 16, acol + (int64_t)shids[h] * lda, 16u);
     }
   };
   cp_async_wait_all();
+  if (warp < NPW) round_own_chunks(min(32, Cin));
   if (warp == NPW) tmem_alloc<NT>(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -330,111 +356,134 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     const int q = warp & 3, g = warp >> 2;          // TMEM lane quarter, A slot
     const int r = q * 32 + lane;                    // this thread's tile row = TMEM lane
     const uint32_t a_tm = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a_col0 + 64 * g);
+    const uint32_t lm_r = base + L.lmap_off + 2u * (uint32_t)r;   // lmap[k][r] at lm_r + 256 k
+    const uint32_t hcap_u = (uint32_t)hcap;
     bool dirty = true;                              // the slot holds data in some row of this warp
     int v2 = g;                                     // next slot visit of this warp
+    uint32_t eph = 0;                               // phase of `empty[g]` this warp's next visit waits for (^1: first pass free)
+    int wslot = 0, st_prev = 0;                     // weight-ring slot / phase of the visit's first stage (quarter 0 only)
+    uint32_t wph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int cvalid = min(32, Cin - kb * 32);    // live channels of this block (multiple of 8)
+      const bool wide = cvalid > 16;
       if (kb > 0) {
         named_bar_sync(1, 32 * NPW);   // every builder has finished reading the previous channel block's halo
         if (tid == 0) SCN_TL(32 + 2 * kb);
         load_halo(kb);
         cp_async_wait_all();
+        round_own_chunks(cvalid);
         named_bar_sync(1, 32 * NPW);   // halo complete and visible to all builders
         if (tid == 0) SCN_TL(33 + 2 * kb);
       }
       const int v2_end = (kb + 1) * nk2;
-      // Software pipeline: the first 16 channels of the warp's NEXT visit are read from the halo into registers while the
-      // tensor pipe still owns the slot; the rest follows right after "slot free", under the first TMEM store.
+      // State of the warp's NEXT visit, set by prefetch(): row bases of the two offsets' halo rows (absent neighbours and
+      // rows beyond the halo capacity both map to the all-zero row `hcap`: min(slot, hcap), since the two markers are the
+      // largest 16-bit values), flags (bit 0: some row of the warp has a neighbour, bit 1: some row lies beyond the halo
+      // capacity and is fetched through the global neighbour map -- rare), and the first 16 channels of the first offset,
+      // read while the tensor pipe still owns the slot.
       float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
-      uint32_t slot0 = kAbsent, slot1 = kAbsent;
+      uint32_t rb0 = 0, rb1 = 0, fl = 0, s0 = kAbsent, s1 = kAbsent;
       int k0 = 0, k1 = 0;
-      bool any = false;
-      // Branch-free: absent neighbours read the all-zero row (halo row `hcap`, one broadcast address); rows beyond the halo
-      // capacity read it too and are then fetched through the global neighbour map under a warp-uniform test (rare).
-      bool ovf = false;
-      auto load_half = [&](uint32_t slot, int k, int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
-        if (dbg & 5) return;   // knockout experiment (b200scn_set_option "halo_dbg"): no halo reads
-        const uint32_t rowi = slot < kOverflow ? slot : (uint32_t)hcap;
-        const uint32_t rb = halo_base + rowi * 128;
-        if (dbg & 128) {   // experiment: absent lanes issue no shared-memory access
-          const bool pr = slot < kOverflow;
-          a0 = lds_f4_if(rb + (((rowi + 4 * hf + 0) & 7u) << 4), pr);
-          a1 = lds_f4_if(rb + (((rowi + 4 * hf + 1) & 7u) << 4), pr);
-          a2 = lds_f4_if(rb + (((rowi + 4 * hf + 2) & 7u) << 4), pr);
-          a3 = lds_f4_if(rb + (((rowi + 4 * hf + 3) & 7u) << 4), pr);
-        } else {
-        a0 = lds_f4(rb + (((rowi + 4 * hf + 0) & 7u) << 4));
-        a1 = lds_f4(rb + (((rowi + 4 * hf + 1) & 7u) << 4));
-        a2 = lds_f4(rb + (((rowi + 4 * hf + 2) & 7u) << 4));
-        a3 = lds_f4(rb + (((rowi + 4 * hf + 3) & 7u) << 4));
+      bool two = false;
+      // (rare) this lane's row of offset k lies beyond the halo capacity: its 16 channels [hf*16, +16) from global
+      auto fetch_overflow = [&](int k, int hf, float4 &a0, float4 &a1, float4 &a2, float4 &a3) {
+        const int idx = __ldg(nbr + (int64_t)sorow[r] * 27 + k);
+        const float *src = A + (int64_t)idx * lda + (kb * 32 + hf * 16);
+        a0 = ldg_f4(src);
+        a1 = ldg_f4(src + 4);
+        if (hf * 16 + 8 < cvalid) {
+          a2 = ldg_f4(src + 8);
+          a3 = ldg_f4(src + 12);
         }
-        if (ovf && slot == kOverflow) {
-          const int idx = __ldg(nbr + (int64_t)sorow[r] * 27 + k);
-          const float *src = A + (int64_t)idx * lda + (kb * 32 + hf * 16);
-          a0 = ldg_f4(src);
-          a1 = ldg_f4(src + 4);
-          if (hf * 16 + 8 < cvalid) {
-            a2 = ldg_f4(src + 8);
-            a3 = ldg_f4(src + 12);
-          }
-        }
-        if (round_a) { rna4(a0); rna4(a1); rna4(a2); rna4(a3); }   // (skipped when the producer already rounded the rows)
+        if (round_a) { rna4(a0); rna4(a1); rna4(a2); rna4(a3); }
       };
+#define SCN_LOAD_HALF(rb, HF, a0, a1, a2, a3)                                      \
+  do {                                                                             \
+    if (!(DBG && (dbg & 5))) {                                                     \
+      a0 = lds_f4_at<64 * (HF) + 0>(rb);                                           \
+      a1 = lds_f4_at<64 * (HF) + 16>(rb);                                          \
+      a2 = lds_f4_at<64 * (HF) + 32>(rb);                                          \
+      a3 = lds_f4_at<64 * (HF) + 48>(rb);                                          \
+    }                                                                              \
+  } while (0)
       auto prefetch = [&](int v2_) {
         const int ki = 2 * (v2_ - kb * nk2);
         k0 = klist[ki];
-        slot0 = slmap[k0 * kTile + r];
-        slot1 = kAbsent;
-        if (ki + 1 < nk) {
+        s0 = lds_u16(lm_r + 256u * (uint32_t)k0);
+        s1 = kAbsent;
+        two = ki + 1 < nk;
+        if (two) {
           k1 = klist[ki + 1];
-          slot1 = slmap[k1 * kTile + r];
+          s1 = lds_u16(lm_r + 256u * (uint32_t)k1);
         }
-        any = __any_sync(0xffffffffu, (slot0 & slot1) != kAbsent);
-        ovf = __any_sync(0xffffffffu, slot0 == kOverflow || slot1 == kOverflow);
-        load_half(slot0, k0, 0, p0, p1, p2, p3);
+        fl = __reduce_or_sync(0xffffffffu, ((s0 & s1) != kAbsent ? 1u : 0u) | ((s0 == kOverflow || s1 == kOverflow) ? 2u : 0u));
+        rb0 = halo_base + min(s0, hcap_u) * kHaloPitch;
+        rb1 = halo_base + min(s1, hcap_u) * kHaloPitch;
+        SCN_LOAD_HALF(rb0, 0, p0, p1, p2, p3);
+        if ((fl & 2u) && s0 == kOverflow) fetch_overflow(k0, 0, p0, p1, p2, p3);
       };
       if (v2 < v2_end) prefetch(v2);
       for (; v2 < v2_end; v2 += NS) {
-        const int ki = 2 * (v2 - kb * nk2);
-        const bool two = ki + 1 < nk;
-        if (q == 0 && lane == 0) {
-          // quarter 0 also vouches for the visit's weight slices, so the MMA thread polls ONE barrier per visit
-          const int st = kb * nk + ki;
-          mbar_wait(wfull + st % nw, (uint32_t)(st / nw) & 1u);
-          if (two) mbar_wait(wfull + (st + 1) % nw, (uint32_t)((st + 1) / nw) & 1u);
-        }
-        mbar_wait(empty + g, ((uint32_t)(v2 / NS) & 1u) ^ 1u);
-        tc_fence_after();
-        if (q == 0 && v2 / NS < 128) SCN_TL(64 + g * 256 + 2 * (v2 / NS));
-        if ((any || dirty) && !(dbg & 1)) {
-          // (measured, no gain: a second register set so that the next half-row's reads fly under the previous TMEM store)
-          float4 u0 = p0, u1 = p0, u2 = p0, u3 = p0;
-          if (cvalid > 16) {
-            load_half(slot0, k0, 1, u0, u1, u2, u3);
-            if (!(dbg & 8)) tmem_st16(a_tm, p0, p1, p2, p3);
-            if (!(dbg & 8)) tmem_st16(a_tm + 16, u0, u1, u2, u3);
-          } else {
-            if (!(dbg & 8)) tmem_st16(a_tm, p0, p1, p2, p3);
-          }
-          if (two) {
-            load_half(slot1, k1, 0, u0, u1, u2, u3);
-            if (!(dbg & 8)) tmem_st16(a_tm + 32, u0, u1, u2, u3);
-            if (cvalid > 16) {
-              load_half(slot1, k1, 1, u0, u1, u2, u3);
-              if (!(dbg & 8)) tmem_st16(a_tm + 48, u0, u1, u2, u3);
+        if (q == 0) {
+          // quarter 0 also vouches for the visit's weight slices, so the MMA thread polls ONE barrier per visit.
+          // Ring slot and phase of the visit's first stage are tracked incrementally (no division in the loop).
+          const int st = kb * nk + 2 * (v2 - kb * nk2);
+          wslot += st - st_prev;
+          st_prev = st;
+          while (wslot >= nw) { wslot -= nw; wph ^= 1u; }
+          if (lane == 0) {
+            mbar_wait(wfull + wslot, wph);
+            if (two) {
+              const bool wrap = wslot + 1 == nw;
+              mbar_wait(wfull + (wrap ? 0 : wslot + 1), wph ^ (wrap ? 1u : 0u));
             }
           }
-          if (q == 0 && v2 / NS < 128) SCN_TL(2200 + g * 512 + 4 * (v2 / NS));
+        }
+        mbar_wait(empty + g, eph ^ 1u);
+        eph ^= 1u;
+        tc_fence_after();
+        if (DBG && q == 0 && v2 / NS < 128) SCN_TL(64 + g * 256 + 2 * (v2 / NS));
+        const bool any = (fl & 1u) != 0;
+        if ((any || dirty) && !(DBG && (dbg & 1))) {
+          // 32 data registers: while one half-row (16 channels) is being stored to tensor memory the next is being read
+          const bool st_on = !(DBG && (dbg & 8));
+          const bool ovf = (fl & 2u) != 0;
+          if (wide) {
+            float4 u0, u1, u2, u3;
+            SCN_LOAD_HALF(rb0, 1, u0, u1, u2, u3);
+            if (ovf && s0 == kOverflow) fetch_overflow(k0, 1, u0, u1, u2, u3);
+            if (st_on) tmem_st16(a_tm, p0, p1, p2, p3);
+            if (two) {
+              SCN_LOAD_HALF(rb1, 0, p0, p1, p2, p3);
+              if (ovf && s1 == kOverflow) fetch_overflow(k1, 0, p0, p1, p2, p3);
+            }
+            if (st_on) tmem_st16(a_tm + 16, u0, u1, u2, u3);
+            if (two) {
+              SCN_LOAD_HALF(rb1, 1, u0, u1, u2, u3);
+              if (ovf && s1 == kOverflow) fetch_overflow(k1, 1, u0, u1, u2, u3);
+              if (st_on) tmem_st16(a_tm + 32, p0, p1, p2, p3);
+              if (st_on) tmem_st16(a_tm + 48, u0, u1, u2, u3);
+            }
+          } else {
+            if (st_on) tmem_st16(a_tm, p0, p1, p2, p3);
+            if (two) {
+              SCN_LOAD_HALF(rb1, 0, p0, p1, p2, p3);
+              if (ovf && s1 == kOverflow) fetch_overflow(k1, 0, p0, p1, p2, p3);
+              if (st_on) tmem_st16(a_tm + 32, p0, p1, p2, p3);
+            }
+          }
+          if (DBG && q == 0 && v2 / NS < 128) SCN_TL(2200 + g * 512 + 4 * (v2 / NS));
           tmem_st_wait();
-          if (q == 0 && v2 / NS < 128) SCN_TL(2201 + g * 512 + 4 * (v2 / NS));
+          if (DBG && q == 0 && v2 / NS < 128) SCN_TL(2201 + g * 512 + 4 * (v2 / NS));
         }
         dirty = any || !two;   // (a one-stage visit leaves the slot's second half as it was)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(full + g);
-        if (q == 0 && v2 / NS < 128) SCN_TL(65 + g * 256 + 2 * (v2 / NS));
+        if (DBG && q == 0 && v2 / NS < 128) SCN_TL(65 + g * 256 + 2 * (v2 / NS));
         if (v2 + NS < v2_end) prefetch(v2 + NS);
       }
+#undef SCN_LOAD_HALF
     }
     // successor tile's first halo block -> L2 (its ids were prefetched at the start of this CTA and are L2 hits by now)
     if (pf_on) {
@@ -447,9 +496,10 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     if (lane == 0) {
       int s = 0, ki = 0, kb = 0;
       uint32_t ph = 0;
+      const uint32_t tx = (DBG && (dbg & 64)) ? b_bytes >> 1 : b_bytes;   // (64: experiment, half the W bytes)
       for (int it = 0; it < T; ++it) {
         if ((s & 1) == 0) mbar_wait(wempty + (s >> 1), ph ^ 1u);   // pair (s, s+1) consumed by the tensor pipe
-        mbar_arrive_expect_tx(wfull + s, (dbg & 64) ? b_bytes >> 1 : b_bytes);   // (64: experiment, half the W bytes)
+        mbar_arrive_expect_tx(wfull + s, tx);
         tma_load_2d(b_base + (uint32_t)s * b_bytes, &tmW, kb * 32, klist[ki] * w_rows_per_k + w_row0, wfull + s);
         if (++ki == nk) { ki = 0; ++kb; }
         if (++s == nw) { s = 0; ph ^= 1u; }
@@ -468,7 +518,7 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     int ws = 0, s = 0;
     uint32_t b_lo = b_lo0, ph = 0, accf = 0;
     auto stage = [&](uint32_t a_tm, int nj) {
-      if (dbg & 2) {
+      if (DBG && (dbg & 2)) {
       } else if (nj == 4) {
         mma_tf32_ts(tmem, a_tm, desc_hi | (uint64_t)b_lo, idesc, accf);
         mma_tf32_ts(tmem, a_tm + 8, desc_hi | (uint64_t)(b_lo + 2), idesc, 1u);
@@ -488,16 +538,16 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
     for (int kb = 0; kb < nkb; ++kb) {
       const int nj = kb == nkb - 1 ? nj_last : 4;
       for (int p = 0; p < nk2; ++p) {
-        if (kb == 0 && p < 64) SCN_TL(1088 + 4 * p);
+        if (DBG && kb == 0 && p < 64) SCN_TL(1088 + 4 * p);
         mbar_wait(full + s, ph);   // A slot written AND its W slices landed
         tc_fence_after();
-        if (kb == 0 && p < 64) SCN_TL(1089 + 4 * p);
+        if (DBG && kb == 0 && p < 64) SCN_TL(1089 + 4 * p);
         const uint32_t a_tm = a_tm0 + 64 * s;
         stage(a_tm, nj);
         if (2 * p + 1 < nk) stage(a_tm + 32, nj);
-        if (kb == 0 && p < 64) SCN_TL(1090 + 4 * p);
+        if (DBG && kb == 0 && p < 64) SCN_TL(1090 + 4 * p);
         mma_commit(empty + s);
-        if (kb == 0 && p < 64) SCN_TL(1091 + 4 * p);
+        if (DBG && kb == 0 && p < 64) SCN_TL(1091 + 4 * p);
         if (++s == NS) { s = 0; ph ^= 1u; }
       }
     }
@@ -524,11 +574,20 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      if (row >= 0 && !(dbg & 32)) {
+      if (row >= 0 && !(DBG && (dbg & 32))) {
         if (addend) {
-          const float *ad = addend + (int64_t)row * ldadd + c0;
+          const float4 *ad = reinterpret_cast<const float4 *>(addend + (int64_t)row * ldadd + c0);
+          if (((ldadd & 3) == 0) && ((reinterpret_cast<uintptr_t>(addend) & 15) == 0)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += __ldg(ad + i);
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = __ldg(ad + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          } else {
+            const float *as = addend + (int64_t)row * ldadd + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(as + i);
+          }
         }
         float *o = out + (int64_t)row * ldo + c0;
         if (vec) {
@@ -548,13 +607,13 @@ halo_conv_tc_kernel(const __grid_constant__ CUtensorMap tmW, const float *__rest
   if (warp == NPW) tmem_dealloc<NT>(tmem);
 }
 
-template <uint32_t NT, int NS, int MINB>
+template <uint32_t NT, int NS, int MINB, bool DBG>
 static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, const float *A, int64_t lda,
                        const int32_t *nbr, const int32_t *perm, const uint16_t *lmap, const int32_t *halo_ids,
                        const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n, const float *Wkm, int Cin,
                        int Cout, const float *addend, int64_t ldadd, float *out, int64_t ldo, int w_rows_per_k,
                        int w_row0, int round_a, cudaStream_t st) {
-  auto kern = halo_conv_tc_kernel<NT, NS, MINB>;
+  auto kern = halo_conv_tc_kernel<NT, NS, MINB, DBG>;
   static int smem_set = 0;   // per template instantiation: the attribute only ever needs to grow
   if ((int)L.total > smem_set) {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -570,6 +629,8 @@ static int launch_halo(int64_t tiles, const HaloSmem &L, int nw, int acc_cols, c
   return 0;
 }
 
+static bool g_timeline_on = false;   // host mirror of g_timeline != nullptr
+
 static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const int32_t *perm, const uint16_t *lmap,
                           const int32_t *halo_ids, const int32_t *halo_n, const uint32_t *kmask, int hcap, int64_t n,
                           const float *Wkm, int Cin, int Cout, const float *addend, int64_t ldadd, float *out,
@@ -579,7 +640,8 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
   // it too: three slots up to Cout = 64, two up to Cout = 128.  The weight ring takes whatever shared memory is left, up
   // to kHaloMaxW slots; with a large halo capacity the same kernel simply runs one CTA per SM.
   const int acc_cols = (Cout + 31) & ~31;
-  const uint32_t half = (227 * 1024) / 2 - 1024, whole = 227 * 1024;
+  // 228 KB of shared memory per SM, 1 KB of it reserved per resident CTA: two CTAs fit when each asks for <= 113 KB
+  const uint32_t half = (228 * 1024) / 2 - 1024, whole = 227 * 1024;
   // The weight ring must hold every stage the A slots can have in flight (NS slots x 2 stages): a builder vouches for its
   // visit's weight slices through a PARITY wait on wfull, and a parity wait on a ring slot that is a whole ring cycle behind
   // succeeds on the previous cycle's completion -- the MMA then reads the previous stage's weights (found by
@@ -601,8 +663,9 @@ static int halo_conv_part(const float *A, int64_t lda, const int32_t *nbr, const
   const int64_t tiles = ceil_div(n, kTile);
   int rc;
 #define SCN_ARGS tiles, L, nw, acc_cols, A, lda, nbr, perm, lmap, halo_ids, halo_n, kmask, hcap, n, Wkm, Cin, Cout, addend, ldadd, out, ldo, w_rows_per_k, w_row0, round_a, st
-  if (acc_cols <= 64) rc = launch_halo<256, 3, 2>(SCN_ARGS);
-  else rc = launch_halo<256, 2, 2>(SCN_ARGS);
+  const bool dbg_inst = g_opt.halo_dbg != 0 || g_timeline_on;   // knockout switches / timeline probes compiled in
+  if (acc_cols <= 64) rc = dbg_inst ? launch_halo<256, 3, 2, true>(SCN_ARGS) : launch_halo<256, 3, 2, false>(SCN_ARGS);
+  else rc = dbg_inst ? launch_halo<256, 2, 2, true>(SCN_ARGS) : launch_halo<256, 2, 2, false>(SCN_ARGS);
 #undef SCN_ARGS
   if (rc) return rc;
   SCN_CHECK_LAUNCH("subm_conv_tiled");
@@ -620,6 +683,7 @@ extern "C" {
  * that owns `tile` into buf (1600 int64, device); buf = NULL switches it off */
 int b200scn_debug_timeline(long long *buf, int tile) {
   SCN_CUDA(cudaMemcpyToSymbol(g_timeline, &buf, sizeof(buf)));
+  g_timeline_on = buf != nullptr;
   SCN_CUDA(cudaMemcpyToSymbol(g_timeline_tile, &tile, sizeof(tile)));
   return 0;
 }

@@ -18,7 +18,7 @@ if len(sys.argv) > 3:
     shapes = [tuple(a[i:i + 3]) for i in range(0, len(a), 3)]
 CASES = [("full", 0), ("no A build", 1), ("no MMA", 2), ("no A build, no MMA", 3), ("no halo LDS", 4), ("no TMEM st", 8),
          ("no global halo copy", 16), ("no output store", 32), ("no build/MMA/copy/store", 1 | 2 | 16 | 32), ("half W bytes", 64), ("half W, no build/MMA/copy/store", 64 | 1 | 2 | 16 | 32),
-         ("predicated LDS", 128), ("one CTA/SM", -1), ("one CTA/SM skeleton", -(1 | 2 | 16 | 32))]
+         ("one CTA/SM", -1), ("one CTA/SM skeleton", -(1 | 2 | 16 | 32))]
 for cin, cout, lvl in shapes:
     level = md.levels[4096 >> lvl]
     f = torch.randn(level.n, cin, device='cuda')
