@@ -24,7 +24,8 @@ int grouped_conv_tc(const float *A, int64_t lda, const int32_t *in_rows, const i
                     cudaStream_t st);
 bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t ldg, int Ca, int Cg);
 int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a, const int32_t *pair_g,
-               const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg, float *dW, cudaStream_t st);
+               const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg, float *dW, cudaStream_t st,
+               const int32_t *blk_tab = nullptr, int nblk = 0);
 }  // namespace b200scn
 
 using namespace b200scn;
@@ -88,6 +89,15 @@ int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, co
   return pair_dw_simt(A, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, Ca, Cg, dW, (cudaStream_t)stream);
 }
 
+int b200scn_pair_dw_blocked(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                            const int32_t *pair_g, const int32_t *blk_offsets, int K, int nblk, int Ca, int Cg,
+                            float *dW, void *stream) {
+  if (K < 1 || K > 64 || nblk < 1 || !blk_offsets) return set_error("pair_dw_blocked: bad K=%d / nblk=%d / table", K, nblk);
+  if (!pair_dw_tc_supported(A, lda, G, ldg, Ca, Cg))
+    return set_error("pair_dw_blocked: shape %d x %d not taken by the tensor-core kernel (use b200scn_pair_dw)", Ca, Cg);
+  return pair_dw_tc(A, lda, G, ldg, pair_a, pair_g, nullptr, K, 1, Ca, Cg, dW, (cudaStream_t)stream, blk_offsets, nblk);
+}
+
 }  // extern "C"
 
 /* 1 if b200scn_gather_conv(precision = 1) accepts this shape */
@@ -103,6 +113,8 @@ extern "C" int b200scn_set_option(const char *name, int value) {
   else if (!strcmp(name, "tc_msub")) g_opt.tc_msub = value;
   else if (!strcmp(name, "tc_nsplit")) g_opt.tc_nsplit = value;
   else if (!strcmp(name, "dw_chunk")) g_opt.dw_chunk = value >= 512 ? value : 512;
+  else if (!strcmp(name, "dw_pairs")) g_opt.dw_pairs = value == 64 ? 64 : 32;
+  else if (!strcmp(name, "dw_dbg")) g_opt.dw_dbg = value;
   else if (!strcmp(name, "halo_pf")) g_opt.halo_pf = value;
   else if (!strcmp(name, "halo_dbg")) g_opt.halo_dbg = value;
   else if (!strcmp(name, "halo_one_cta")) g_opt.halo_one_cta = value;

@@ -33,6 +33,8 @@ struct Options {
   int tc_msub = 0;       // 0 auto, 1 / 2: accumulators per CTA of the gather kernel
   int tc_nsplit = 0;     // 0 auto, >0: split the offsets of the gather kernel over this many CTAs
   int dw_chunk = 4096;   // pairs per CTA of the pair-list weight-gradient kernel
+  int dw_pairs = 32;     // pairs per pipeline stage of that kernel (32 or 64)
+  int dw_dbg = 0;        // knockout experiments of that kernel (WRONG RESULTS): 1 no MMA issue, 2 no gathers
   int halo_pf = -1;      // L2 prefetch distance of the tiled kernel in tiles (-1 auto, 0 off)
   int halo_dbg = 0;      // knockout experiments of the tiled kernel (WRONG RESULTS): 1 no A build, 2 no MMA, 4 no halo reads, 8 no TMEM stores
   int halo_one_cta = 0;  // 1: force one CTA per SM in the tiled kernel

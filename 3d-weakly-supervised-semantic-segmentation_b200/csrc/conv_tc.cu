@@ -513,18 +513,19 @@ static int gather_conv_tc_part(const float *A, int64_t lda, const int32_t *map, 
 // =====================================================================================================================
 namespace b200scn {
 
-constexpr int kDwPairs = 32;  // pairs per stage (4 MMAs of K = 8)
+// PAIRS (template): pairs per stage, 32 or 64 (4 or 8 MMAs of K = 8 per stage and 128-channel tile)
 constexpr int kDwWarps = 16;  // producer warps, four per stage
 
 // A stage holds only the VALID 32-channel blocks of A (ab of them) followed by the gb blocks of G.  The M = 128 MMA of
 // tile t still reads four MN blocks starting at block 4t; blocks past Ca alias whatever follows in shared memory
 // (G blocks, the next stage, the tail pad) -- finite or not, they only feed accumulator rows >= Ca, which are never read.
-template <uint32_t NT>
+template <uint32_t NT, int PAIRS>
 __global__ void __launch_bounds__(32 * (kDwWarps + 1))
 pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ G, int64_t ldg,
                   const int32_t *__restrict__ pair_a, const int32_t *__restrict__ pair_g,
                   const int32_t *__restrict__ offsets, int n_single, int chunk, int Ca, int Cg, int nstages,
-                  uint32_t idesc, float *__restrict__ dW, int64_t dw_kstride) {
+                  uint32_t idesc, float *__restrict__ dW, int64_t dw_kstride, const int32_t *__restrict__ blk_tab, int nblk,
+                  uint32_t pad_bytes, int dbg) {
   constexpr int NPW = kDwWarps;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -533,11 +534,11 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   const int mt = (Ca + 127) >> 7;            // 128-channel M tiles
   const int ab = (Ca + 31) >> 5;             // valid 32-channel blocks of A
   const int gb = (Cg + 31) >> 5;
-  const uint32_t blk = kDwPairs * 128;       // one 32-channel block of one stage: 32 pair rows x 128 B
+  const uint32_t blk = PAIRS * 128;       // one 32-channel block of one stage: 32 pair rows x 128 B
   const uint32_t a_bytes = (uint32_t)ab * blk, g_bytes = (uint32_t)gb * blk;
   const uint32_t stage_bytes = a_bytes + g_bytes;
   // barriers sit after the stages and a 3-block pad (the aliasing reads above may run 3 blocks past the last stage)
-  uint64_t *full = reinterpret_cast<uint64_t *>(sm + (uint32_t)nstages * stage_bytes + 3 * blk);
+  uint64_t *full = reinterpret_cast<uint64_t *>(sm + (uint32_t)nstages * stage_bytes + pad_bytes);
   uint64_t *empty = full + kMaxStages;
   uint64_t *accum = empty + kMaxStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum + 1);
@@ -546,17 +547,25 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   // offsets vary fastest over the grid: CTAs resident at the same time work on the same stretch of every offset's list,
   // i.e. (with Morton-ordered lists) on the same region of space, so gathered rows are shared in L2
   const int k = blockIdx.x;
-  const int beg = offsets ? offsets[k] : 0;
-  const int end = offsets ? offsets[k + 1] : n_single;
-  const int p0 = beg + blockIdx.y * chunk;
-  const int p1 = min(p0 + chunk, end);
+  int p0, p1;
+  if (blk_tab) {
+    // one CTA per (offset, row block) of a b200scn_pair_lists_blocked table: block b of every offset is the same stretch of
+    // the Morton curve, so the CTAs resident at the same time (offsets vary fastest over the grid) gather the same rows
+    p0 = __ldg(blk_tab + (int64_t)k * nblk + blockIdx.y);
+    p1 = __ldg(blk_tab + (int64_t)k * nblk + blockIdx.y + 1);
+  } else {
+    const int beg = offsets ? offsets[k] : 0;
+    const int end = offsets ? offsets[k + 1] : n_single;
+    p0 = beg + blockIdx.y * chunk;
+    p1 = min(p0 + chunk, end);
+  }
   if (p0 >= p1) return;  // uniform for the whole CTA
-  const int T = (p1 - p0 + kDwPairs - 1) / kDwPairs;
+  const int T = (p1 - p0 + PAIRS - 1) / PAIRS;
   const int wps = NPW / nstages;  // producer warps per stage (nstages is 2 or 4)
 
   if (tid == 0) {
     for (int s = 0; s < nstages; ++s) {
-      mbar_init(full + s, 32 * wps);
+      mbar_init(full + s, wps);   // one arrival per producer warp (128 lanes arriving one by one on the same word cost ~500 cycles per stage)
       mbar_init(empty + s, 1);
     }
     mbar_init(accum, 1);
@@ -569,59 +578,67 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
   const uint32_t tmem = *tmem_slot;
 
   if (warp < NPW) {
-    // producers: stage s is always filled by warps s, s + nstages, ... (each takes an equal share of the 32 pairs)
+    // producers: stage s is always filled by warps s, s + nstages, ... (each takes an equal share of the 32 pairs).
+    // The loop is bound by instruction issue and copy latency (ncu: ~220 instructions per warp and stage before this
+    // rewrite, half of all issue slots), so everything that does not depend on the pair is computed once: the swizzled
+    // shared-memory offset of each of the lane's rows, the channel-block masks, the stage's base address; the ring phase
+    // is toggled instead of divided out.
     const int c = lane & 7, rl = lane >> 3;
-    const int my_stage = warp % nstages, part = warp / nstages;
-    const int rows_per_warp = kDwPairs / wps;
+    const int lg = nstages == 4 ? 2 : 1;          // nstages is 2 or 4
+    const int my_stage = warp & (nstages - 1), part = warp >> lg;
+    const int rows_per_warp = PAIRS / wps;
+    constexpr int kMaxSlots = PAIRS / 16;   // slots per lane with four producer warps per stage (nstages = 4); half of them with eight
+    const int nslots = rows_per_warp / 4;
+    uint32_t soff[kMaxSlots];
+#pragma unroll
+    for (int i = 0; i < kMaxSlots; ++i) soff[i] = sw128_32b((uint32_t)(part * rows_per_warp + rl + 4 * i), (uint32_t)c);
+    // channel blocks this lane's 16-byte chunk exists in (the last block of a width that is not a multiple of 32 is partial)
+    const int na = min(ab, (Ca - c * 4 + 31) >> 5), ng = min(gb, (Cg - c * 4 + 31) >> 5);
+    const uint32_t a_st = base + (uint32_t)my_stage * stage_bytes, g_st = a_st + a_bytes;
+    const float *Ac = A + c * 4, *Gc = G + c * 4;
     // the pair indices of the NEXT iteration are fetched while the current one is being staged (the index load ->
     // address -> copy chain is otherwise a serial global round trip at the head of every stage)
-    constexpr int kMaxSlots = kDwPairs / 4 / 2;   // slots per lane at the smallest warps-per-stage (2)
     int nra[kMaxSlots], nrg[kMaxSlots];
-    const int nslots = rows_per_warp / 4;
+    const int pl = p0 + part * rows_per_warp + rl;
     auto fetch = [&](int it_) {
-      const int pb = p0 + it_ * kDwPairs;
+      const int pb = pl + it_ * PAIRS;
 #pragma unroll
       for (int i = 0; i < kMaxSlots; ++i) {
         if (i < nslots) {
-          const int p = pb + part * rows_per_warp + rl + 4 * i;
-          const bool live = it_ < T && p < p1;
+          const int p = pb + 4 * i;
+          const bool live = p < p1;
           nra[i] = live ? (pair_a ? __ldg(pair_a + p) : p) : -1;
           nrg[i] = live ? (pair_g ? __ldg(pair_g + p) : p) : -1;
         }
       }
     };
     fetch(my_stage);
+    uint32_t ph = 1;   // parity of `empty` to wait for (first pass: the slot is free)
     for (int it = my_stage; it < T; it += nstages) {
-      const int s = my_stage;
-      const uint32_t ph = (uint32_t)(it / nstages) & 1u;
       int cra[kMaxSlots], crg[kMaxSlots];
 #pragma unroll
       for (int i = 0; i < kMaxSlots; ++i) { cra[i] = nra[i]; crg[i] = nrg[i]; }
       fetch(it + nstages);
-      mbar_wait(empty + s, ph ^ 1u);
-      const uint32_t a_st = base + (uint32_t)s * stage_bytes, g_st = a_st + a_bytes;
+      mbar_wait(empty + my_stage, ph);
+      ph ^= 1u;
 #pragma unroll
       for (int i = 0; i < kMaxSlots; ++i) {
         if (i >= nslots) break;
-        const int r = part * rows_per_warp + rl + 4 * i;
         const bool live = cra[i] >= 0;
-        const int ra = live ? cra[i] : 0;
-        const int rg = live ? crg[i] : 0;
-        const float *arow = A + (int64_t)ra * lda + c * 4;
-        const float *grow = G + (int64_t)rg * ldg + c * 4;
-        const uint32_t off = sw128_32b(r, c);
-        for (int b = 0; b < ab; ++b) {
-          const bool ok = live && (b * 32 + c * 4 < Ca);
-          cp_async16(a_st + (uint32_t)b * blk + off, ok ? (const void *)(arow + b * 32) : (const void *)A, ok ? 16u : 0u);
-        }
-        for (int b = 0; b < gb; ++b) {
-          const bool ok = live && (b * 32 + c * 4 < Cg);
-          cp_async16(g_st + (uint32_t)b * blk + off, ok ? (const void *)(grow + b * 32) : (const void *)G, ok ? 16u : 0u);
-        }
+        const uint32_t sz = live ? 16u : 0u;      // a dead pair (list tail) zero-fills its rows
+        const float *arow = Ac + (int64_t)(live ? cra[i] : 0) * lda;
+        const float *grow = Gc + (int64_t)(live ? crg[i] : 0) * ldg;
+        const uint32_t so = soff[i];
+        if (dbg & 2) continue;   // knockout experiment (b200scn_set_option "dw_dbg"): no gathers
+        for (int b = 0; b < na; ++b) cp_async16(a_st + (uint32_t)b * blk + so, arow + b * 32, sz);
+        for (int b = na; b < ab; ++b) cp_async16(a_st + (uint32_t)b * blk + so, A, 0u);
+        for (int b = 0; b < ng; ++b) cp_async16(g_st + (uint32_t)b * blk + so, grow + b * 32, sz);
+        for (int b = ng; b < gb; ++b) cp_async16(g_st + (uint32_t)b * blk + so, G, 0u);
       }
       cp_async_wait_all();
       fence_proxy_async();
-      mbar_arrive(full + s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + my_stage);
     }
   } else if (elect_one()) {
     // constant descriptor part once, 32-bit patching of the start address per MMA (see the gather kernel)
@@ -634,9 +651,9 @@ pair_dw_tc_kernel(const float *__restrict__ A, int64_t lda, const float *__restr
       tc_fence_after();
       const uint32_t a_lo = desc_lo0 + ((base + (uint32_t)s * stage_bytes) >> 4);
       const uint32_t g_lo = a_lo + (a_bytes >> 4);
-      for (int t = 0; t < mt; ++t) {
+      for (int t = 0; t < mt && !(dbg & 1); ++t) {   // (dbg 1: knockout experiment, no MMA issue)
 #pragma unroll
-        for (int j = 0; j < kDwPairs / 8; ++j) {
+        for (int j = 0; j < PAIRS / 8; ++j) {
           const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)(4 * t) * (blk >> 4) + j * 64);
           const uint64_t gd = desc_hi | (uint64_t)(g_lo + j * 64);
           mma_tf32(tmem + (uint32_t)(t * Cg), ad, gd, idesc, (it | j) ? 1u : 0u);
@@ -679,13 +696,19 @@ bool pair_dw_tc_supported(const float *A, int64_t lda, const float *G, int64_t l
 // one launch for channels [ca0, ca0 + Ca) of A (the accumulator of a launch must fit the 512 TMEM columns)
 static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
                            const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
-                           float *dW, int64_t dw_kstride, cudaStream_t st) {
+                           float *dW, int64_t dw_kstride, cudaStream_t st, const int32_t *blk_tab = nullptr, int nblk = 0) {
   const int mt = (Ca + 127) >> 7, ab = (Ca + 31) >> 5, gb = (Cg + 31) >> 5;
-  const uint32_t blk = kDwPairs * 128;
+  const int pairs = g_opt.dw_pairs == 64 ? 64 : 32;   // pairs per stage (64 measured 5-20 % slower wherever fewer stages fit)
+  const uint32_t blk = (uint32_t)pairs * 128;
   const uint32_t stage_bytes = (uint32_t)(ab + gb) * blk;
+  // an M = 128 MMA reads four 32-channel blocks of A whatever Ca is: with fewer A blocks the reads run on into the G blocks
+  // of the stage and, in the last stage, past it -- the rows they produce belong to channels >= Ca and are never stored
+  const int over = 4 * mt - ab - gb;
+  const uint32_t pad = over > 0 ? (uint32_t)over * blk : 0u;
   int nstages = kMaxStages;
-  if ((uint32_t)nstages * stage_bytes + 3 * blk + 256 + 1024 > 72 * 1024) nstages = 2;   // keep >= 3 CTAs per SM
-  const uint32_t smem = (uint32_t)nstages * stage_bytes + 3 * blk + 256 + 1024;
+  // registers allow two CTAs per SM: four stages whenever two CTAs of them fit in shared memory (113 KB each)
+  if ((uint32_t)nstages * stage_bytes + pad + 256 + 1024 > 113 * 1024) nstages = 2;
+  const uint32_t smem = (uint32_t)nstages * stage_bytes + pad + 256 + 1024;
   if (smem > 227 * 1024) return set_error("pair_dw_tc: shared memory %u too large", smem);
   // chunk of pairs per CTA: enough CTAs for ~4 per SM overall, a multiple of the stage size
   int64_t want_chunks = ceil_div((int64_t)kNumSMs * 4, (int64_t)K);
@@ -694,20 +717,26 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
   const int64_t chunk_max = g_opt.dw_chunk;   // small chunks keep the region the resident CTAs work on (27 offsets x ~11 chunks) inside L2
   if (chunk > chunk_max) chunk = chunk_max;
   if (ceil_div(n_pairs_max, chunk) > 65535) chunk = ceil_div(n_pairs_max, 65535);
-  chunk = ceil_div(chunk, kDwPairs) * kDwPairs;
+  chunk = ceil_div(chunk, (int64_t)pairs) * pairs;
   dim3 grid((unsigned)K, (unsigned)ceil_div(n_pairs_max, chunk));
+  if (blk_tab) grid.y = (unsigned)nblk;
   const uint32_t idesc = make_idesc_tf32(128, Cg, 1, 1);
   const int cols = mt * Cg;
 #define SCN_LAUNCH_DW(NT)                                                                                        \
   do {                                                                                                           \
-    auto kern = pair_dw_tc_kernel<NT>;                                                                           \
+    if (pairs == 32) SCN_LAUNCH_DW2(NT, 32);                                                                     \
+    else SCN_LAUNCH_DW2(NT, 64);                                                                                 \
+  } while (0)
+#define SCN_LAUNCH_DW2(NT, PR)                                                                                   \
+  do {                                                                                                           \
+    auto kern = pair_dw_tc_kernel<NT, PR>;                                                                       \
     static bool smem_set = false;                                                                                \
     if (!smem_set) {                                                                                             \
       SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));             \
       smem_set = true;                                                                                           \
     }                                                                                                            \
     kern<<<grid, 32 * (kDwWarps + 1), smem, st>>>(A, lda, G, ldg, pair_a, pair_g, offsets_dev, (int)n_pairs_max, \
-                                                  (int)chunk, Ca, Cg, nstages, idesc, dW, dw_kstride);           \
+                                                  (int)chunk, Ca, Cg, nstages, idesc, dW, dw_kstride, blk_tab, nblk, pad, g_opt.dw_dbg); \
   } while (0)
   if (cols <= 32) SCN_LAUNCH_DW(32);
   else if (cols <= 64) SCN_LAUNCH_DW(64);
@@ -715,6 +744,7 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
   else if (cols <= 256) SCN_LAUNCH_DW(256);
   else SCN_LAUNCH_DW(512);
 #undef SCN_LAUNCH_DW
+#undef SCN_LAUNCH_DW2
   SCN_CHECK_LAUNCH("pair_dw_tc");
   count_launch(1);
   return 0;
@@ -722,16 +752,17 @@ static int pair_dw_tc_part(const float *A, int64_t lda, const float *G, int64_t 
 
 int pair_dw_tc(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
                const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max, int Ca, int Cg,
-               float *dW, cudaStream_t st) {
+               float *dW, cudaStream_t st, const int32_t *blk_tab, int nblk) {
   SCN_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)K * Ca * Cg, st));
   if (n_pairs_max <= 0) return 0;
+  if (blk_tab && nblk > 65535) return set_error("pair_dw_blocked: %d row blocks exceed the grid limit", nblk);
   // channel slices of A whose accumulators fit TMEM: 128-channel tiles x Cg columns <= 512
   const int max_tiles = 512 / Cg >= 1 ? 512 / Cg : 1;
   const int slice = 128 * (max_tiles > 4 ? 4 : max_tiles);
   for (int ca0 = 0; ca0 < Ca; ca0 += slice) {
     const int ca = Ca - ca0 < slice ? Ca - ca0 : slice;
     if (pair_dw_tc_part(A + ca0, lda, G, ldg, pair_a, pair_g, offsets_dev, K, n_pairs_max, ca, Cg,
-                        dW + (int64_t)ca0 * Cg, (int64_t)Ca * Cg, st))
+                        dW + (int64_t)ca0 * Cg, (int64_t)Ca * Cg, st, blk_tab, nblk))
       return 1;
   }
   return 0;

@@ -182,9 +182,12 @@ struct PairWriter {
   int64_t n;
   int K;
   int32_t *pair_in, *pair_out, *offsets;
+  int32_t *blk;          // optional: list position at which row block b (row_block rows of `order`) of offset k starts
+  int row_block, nblk;   // row_block is a power of two
   __device__ void operator()(int64_t t, int flag, int pos) const {
     int64_t k = t / n, o = t - k * n;
     if (o == 0) offsets[k] = pos;
+    if (blk && (o & (row_block - 1)) == 0) blk[k * nblk + o / row_block] = pos;
     const int64_t r = order ? order[o] : o;
     if (flag) { pair_in[pos] = map[r * K + k]; pair_out[pos] = (int32_t)r; }
   }
@@ -303,8 +306,29 @@ int b200scn_pair_lists_ordered(const int32_t *map, const int32_t *order, int64_t
   if (n * K >= (int64_t)1 << 31) return set_error("pair_lists: n*K overflows int32");
   if (n <= 0) { SCN_CUDA(cudaMemsetAsync(offsets_dev, 0, sizeof(int32_t) * (K + 1), st)); return 0; }
   PairLoader ld{map, order, n, K};
-  PairWriter wr{map, order, n, K, pair_in, pair_out, offsets_dev};
+  PairWriter wr{map, order, n, K, pair_in, pair_out, offsets_dev, nullptr, 1, 0};
   return scan_flags(ld, wr, n * K, nullptr, (int32_t *)scratch, offsets_dev + K, st);
+}
+
+int b200scn_pair_lists_blocked(const int32_t *map, const int32_t *order, int64_t n, int K, int row_block,
+                               int32_t *pair_in, int32_t *pair_out, int32_t *offsets_dev, int32_t *blk_offsets,
+                               void *scratch, size_t scratch_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_block < 32 || (row_block & (row_block - 1))) return set_error("pair_lists_blocked: row_block %d must be a power of two >= 32", row_block);
+  if (scratch_bytes < b200scn_pair_scratch_bytes(n, K)) return set_error("pair_lists: scratch too small");
+  if (n * K >= (int64_t)1 << 31) return set_error("pair_lists: n*K overflows int32");
+  const int nblk = (int)ceil_div(n > 0 ? n : 1, (int64_t)row_block);
+  if (n <= 0) {
+    SCN_CUDA(cudaMemsetAsync(offsets_dev, 0, sizeof(int32_t) * (K + 1), st));
+    SCN_CUDA(cudaMemsetAsync(blk_offsets, 0, sizeof(int32_t) * ((size_t)K * nblk + 1), st));
+    return 0;
+  }
+  PairLoader ld{map, order, n, K};
+  PairWriter wr{map, order, n, K, pair_in, pair_out, offsets_dev, blk_offsets, row_block, nblk};
+  if (scan_flags(ld, wr, n * K, nullptr, (int32_t *)scratch, offsets_dev + K, st)) return 1;
+  // closing entry = total number of pairs (segment i of the flat table ends where segment i + 1 starts)
+  SCN_CUDA(cudaMemcpyAsync(blk_offsets + (size_t)K * nblk, offsets_dev + K, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return 0;
 }
 
 }  // extern "C"

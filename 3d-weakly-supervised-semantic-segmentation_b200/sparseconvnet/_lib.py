@@ -37,6 +37,7 @@ SIGNATURES = {
     "b200scn_pair_scratch_bytes": (_sz, [_i64, _i32]),
     "b200scn_pair_lists": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200scn_pair_lists_ordered": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200scn_pair_lists_blocked": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "b200scn_gather_conv_tf32_ok": (_i32, [_i32, _i32, _i64]),
     "b200scn_gather_conv": (_i32, [_vp, _i64, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp]),
     "b200scn_morton_keys": (_i32, [_vp, _i64, _vp, _vp]),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "b200scn_group_tiles": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b200scn_grouped_conv": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),
     "b200scn_pair_dw": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp]),
+    "b200scn_pair_dw_blocked": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200scn_unpool": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "b200scn_unpool_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _vp]),
     "b200scn_augment_scratch_bytes": (_sz, [_i64, _i32]),

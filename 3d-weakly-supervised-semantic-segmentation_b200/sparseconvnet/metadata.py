@@ -47,6 +47,7 @@ class Level:
         self.nbr_counts = None    # (27,) int32 device: rules per offset
         self.pairs = None         # (pair_in, pair_out, offsets_dev)
         self.pairs_ordered = None
+        self.pairs_blocked = None
         self._counts = None
         self.plan = None          # TilePlan of the spatially tiled convolution
         self.batch_bits = 15      # sample-index bits sorted by the Morton ordering (InputLayer narrows it to the batch)
@@ -96,6 +97,14 @@ class Level:
             self.pairs_ordered = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()), order=perm)
         return self.pairs_ordered
 
+    def subm_pairs_blocked(self, perm):
+        """Morton-ordered lists plus the row-block table: -> (pair_in, pair_out, offsets, (blk_offsets, nblk))."""
+        if self.pairs_blocked is None:
+            self.pairs_blocked = build_pairs(self.subm_map(), self.n, 27, sum(self.rule_counts()), order=perm,
+                                             row_block=pair_row_block(self.n, 27))
+            self.pairs_ordered = self.pairs_blocked[:3]
+        return self.pairs_blocked
+
 
 class TilePlan:
     """perm (n,) int32 site ids along the Morton curve; lmap (T,27,128) uint16; halo_ids (T,hcap) int32; halo_n, kmask (T,)."""
@@ -127,9 +136,19 @@ class TilePlan:
         _ops._p1(tok)
 
 
-def build_pairs(map_t, n, K, total, order=None):
+def pair_row_block(n, K):
+    """Rows per block of a blocked pair table: a power of two in [1024, 8192] that leaves ~4 CTAs (offset x block) per SM."""
+    want = max(1, (4 * 148 + K - 1) // K)
+    rb = 8192
+    while rb > 1024 and (n + rb - 1) // rb < want:
+        rb //= 2
+    return rb
+
+
+def build_pairs(map_t, n, K, total, order=None, row_block=0):
     """scn-form rulebook (per-offset (in,out) pair lists, ascending out) from a map[n][K] with `total` entries >= 0.
-    `order`: optional int32 permutation of the rows replacing "ascending"."""
+    `order`: optional int32 permutation of the rows replacing "ascending".
+    `row_block` > 0: also return the (K * nblk + 1,) table of row-block boundaries (b200scn_pair_lists_blocked)."""
     dev = map_t.device
     offsets = torch.empty(K + 1, dtype=torch.int32, device=dev)
     nbytes = lib.b200scn_pair_scratch_bytes(n, K)
@@ -139,6 +158,13 @@ def build_pairs(map_t, n, K, total, order=None):
     st = _lib.stream_for(map_t)
     from . import ops as _ops
     tok = _ops._p0("pair_lists", "pair_lists", 2.0 * 4.0 * K * n + 8.0 * total, 0, 0.0, 0.0)   # map read twice + pairs written
+    if row_block:
+        nblk = (max(n, 1) + row_block - 1) // row_block
+        blk = torch.empty(K * nblk + 1, dtype=torch.int32, device=dev)
+        check(lib.b200scn_pair_lists_blocked(ptr(map_t), ptr(order), n, K, row_block, ptr(pair_in), ptr(pair_out),
+                                             ptr(offsets), ptr(blk), ptr(scratch), nbytes, st))
+        _ops._p1(tok)
+        return pair_in, pair_out, offsets, (blk, nblk)
     check(lib.b200scn_pair_lists_ordered(ptr(map_t), ptr(order), n, K, ptr(pair_in), ptr(pair_out), ptr(offsets),
                                          ptr(scratch), nbytes, st))
     _ops._p1(tok)

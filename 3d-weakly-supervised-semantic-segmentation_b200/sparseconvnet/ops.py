@@ -246,6 +246,33 @@ def pair_dw(a, g, pair_a, pair_g, offsets, K, n_pairs_max, rules=None):
     return dw
 
 
+def pair_dw_blocked(a, g, pair_a, pair_g, blk, nblk, K, rules=None):
+    """Same over a b200scn_pair_lists_blocked table: one CTA per (offset, row block).  None if the shape is not taken."""
+    a, lda = _c(a)
+    g, ldg = _c(g)
+    Ca, Cg = a.shape[1], g.shape[1]
+    if not (_precision[0] == 1 and Ca % 4 == 0 and Ca >= 4 and Cg % 16 == 0 and 16 <= Cg <= 256 and lda % 4 == 0
+            and ldg % 4 == 0 and a.data_ptr() % 16 == 0 and g.data_ptr() % 16 == 0):   # = pair_dw_tc_supported (conv_tc.cu)
+        return None
+    dw = torch.empty((K, Ca, Cg), dtype=torch.float32, device=a.device)
+    tok = _p0("pair_dw%d" % K, "pair_dw", 4.0 * (a.shape[0] * Ca + g.shape[0] * Cg) + 4.0 * K * Ca * Cg, rules, 8.0,
+              2.0 * Ca * Cg)
+    check(lib.b200scn_pair_dw_blocked(ptr(a), lda, ptr(g), ldg, ptr(pair_a), ptr(pair_g), ptr(blk), K, nblk, Ca, Cg, ptr(dw),
+                                      _lib.stream_for(a)))
+    _p1(tok)
+    return dw
+
+
+_dw_blocked = [False]
+
+
+def set_blocked_dw(on):
+    """Weight gradient of tiled levels over row-block-aligned pair segments.  Default OFF: measured equal to the per-offset
+    chunks at levels 1-2 and 15-40 % slower at levels 0 and 3 (profiles/r2d_time_dw.txt) -- the kernel is bound by its
+    per-stage synchronisation chain, not by where the gathered rows come from."""
+    _dw_blocked[0] = bool(on)
+
+
 _dw_tiled = [False]
 
 
@@ -300,6 +327,9 @@ class SubmanifoldConvFn(torch.autograd.Function):
             tiled = _precision[0] == 1 and _use_tiled(level.n)
             if tiled and _dw_tiled[0]:
                 dw = subm_dw_tiled(x, g, level)
+            if dw is None and tiled and _dw_blocked[0]:
+                pin, pout, offs, (blk, nblk) = level.subm_pairs_blocked(level.tile_plan(_halo["hcap"]).perm)
+                dw = pair_dw_blocked(x, g, pin, pout, blk, nblk, 27, rules=level)
             if dw is None:
                 if tiled:
                     pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)

@@ -83,6 +83,14 @@ int b200scn_pair_lists(const int32_t *map, int64_t n, int K, int32_t *pair_in, i
 int b200scn_pair_lists_ordered(const int32_t *map, const int32_t *order, int64_t n, int K, int32_t *pair_in,
                                int32_t *pair_out, int32_t *offsets_dev, void *scratch, size_t scratch_bytes,
                                void *stream);
+/* Same lists plus a table of row-block boundaries for the weight-gradient kernel: blk_offsets[k * nblk + b] = position
+ * in the lists at which the pairs of offset k whose row lies in order[b * row_block .. (b+1) * row_block) start
+ * (nblk = ceil(n / row_block), row_block a power of two); blk_offsets has K * nblk + 1 entries, the last = total pairs,
+ * so segment i ends where segment i + 1 starts.  With `order` = the Morton permutation, block b of EVERY offset covers
+ * the same region of space: CTAs (k, b) that run at the same time share their gathered rows in L2. */
+int b200scn_pair_lists_blocked(const int32_t *map, const int32_t *order, int64_t n, int K, int row_block,
+                               int32_t *pair_in, int32_t *pair_out, int32_t *offsets_dev, int32_t *blk_offsets,
+                               void *scratch, size_t scratch_bytes, void *stream);
 
 /* ------------------------------------------------------------------ convolutions (A5-A7, A10) */
 /* out[o,:] = sum_k A[map[o*K+k],:] . W[k]  (+ addend[o,:] if addend)      W: (K,Cin,Cout) row-major.
@@ -167,6 +175,11 @@ int b200scn_scatter_conv(const float *A, int64_t lda, const int32_t *map, int64_
 int b200scn_pair_dw(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
                     const int32_t *pair_g, const int32_t *offsets_dev, int K, int64_t n_pairs_max,
                     int Ca, int Cg, float *dW, int precision, void *stream);
+/* Same with one CTA per (offset k, row block b) of a b200scn_pair_lists_blocked table (tensor-core path only: returns an
+ * error for shapes b200scn_pair_dw would send to the CUDA-core kernel -- call that one then). */
+int b200scn_pair_dw_blocked(const float *A, int64_t lda, const float *G, int64_t ldg, const int32_t *pair_a,
+                            const int32_t *pair_g, const int32_t *blk_offsets, int K, int nblk, int Ca, int Cg,
+                            float *dW, void *stream);
 
 /* out[i,:] = in[parent[i],:]  (UnPooling_updateOutput) and its transpose via the child map. */
 int b200scn_unpool(const float *in, int64_t ldi, const int32_t *parent, int64_t n_fine, int C,

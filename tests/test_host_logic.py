@@ -107,3 +107,55 @@ def test_capacity_rounding_and_scene_generator():
     assert (coords[:offs[1], 3] == 0).all() and (coords[offs[1]:, 3] == 1).all()
     c2, _, _ = make_batch([0, 1], 50, n_points=5000, step=1)
     assert not torch.equal(coords[:100], c2[:100])       # a new step re-randomises the pose
+
+
+def test_checkpoint_with_optimizer_and_scheduler_state(tmp_path):
+    """f4: the reference saves only model.state_dict() (train.py:91) and restarts Adam from zero; the optional
+    optimizer= / scheduler= arguments round-trip the training state too, pruned by the same power-of-two rule."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    sch = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.5)
+    exp = os.path.join(tmp_path, "run")
+    for epoch in (1, 2, 3):
+        net(torch.randn(5, 4)).sum().backward()
+        opt.step(); opt.zero_grad(); sch.step()
+        scn.checkpoint_save(net, exp, "model", epoch, use_cuda=False, optimizer=opt, scheduler=sch)
+    assert sorted(os.listdir(tmp_path)) == sorted(
+        ["run-%09d-model.pth" % e for e in (1, 2, 3)] + ["run-%09d-model.train.pth" % e for e in (1, 2, 3)])
+    scn.checkpoint_save(net, exp, "model", 4, use_cuda=False, optimizer=opt, scheduler=sch)   # epoch 3 is pruned, both files
+    assert not os.path.exists(exp + "-%09d-model.pth" % 3) and not os.path.exists(exp + "-%09d-model.train.pth" % 3)
+    net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1e-3)
+    sch2 = torch.optim.lr_scheduler.StepLR(opt2, step_size=2, gamma=0.5)
+    assert scn.checkpoint_restore(net2, exp, "model", use_cuda=False, optimizer=opt2, scheduler=sch2) == 5
+    s1, s2 = opt.state_dict(), opt2.state_dict()
+    assert s1["param_groups"] == s2["param_groups"]
+    for k in s1["state"]:
+        for name in ("exp_avg", "exp_avg_sq", "step"):
+            assert torch.equal(torch.as_tensor(s1["state"][k][name]), torch.as_tensor(s2["state"][k][name]))
+    assert sch2.state_dict() == sch.state_dict()
+    # the upstream call (no optimizer) still works on the same directory and ignores the .train.pth files
+    assert scn.checkpoint_restore(torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2)), exp, "model",
+                                  use_cuda=False) == 5
+
+
+def test_upstream_keyed_state_dict_loads():
+    """f4: a state_dict with upstream sparseconvnet's key names and shapes (tests/golden/upstream_unet_keys.json:
+    module-tree indices of scn.Sequential/UNet as Function_test.py:113-226 restates them, conv `weight`
+    (filter_volume, 1, nIn, nOut), BatchNorm `weight, bias, runningMean, runningVar` in camelCase) loads
+    strictly into this package's encoder and reaches the right tensors."""
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = json.load(open(os.path.join(here, "golden", "upstream_unet_keys.json")))
+    net = build_encoder(scn, "SparseConvUNet", 16, 1, False)
+    sd = {}
+    for i, (k, shape) in enumerate(spec["keys"]):
+        sd[k] = torch.full(shape, float(i % 97) + 1.0)
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    own = net.state_dict()
+    assert len(own) == len(sd)
+    for i, (k, shape) in enumerate(spec["keys"]):
+        k2 = k.replace("runningMean", "running_mean").replace("runningVar", "running_var")
+        assert tuple(own[k2].shape) == tuple(shape) and float(own[k2].flatten()[0]) == float(i % 97) + 1.0, k
