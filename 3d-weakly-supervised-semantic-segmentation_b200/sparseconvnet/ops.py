@@ -277,9 +277,11 @@ _dw_tiled = [False]
 
 
 def set_tiled_dw(on):
-    """Tile-stationary, bit-reproducible weight gradient (dw_tile.cu) on levels where the tiled forward kernel runs.
-    Default OFF: measured 2.5-3.3x slower than the pair-list kernel on B200 (profiles/r2_dw_tile.md) -- its stages are
-    <= 37 % dense in the reduction dimension and each stage costs a full producer -> MMA -> producer round trip."""
+    """Tile-stationary, bit-reproducible weight gradient (dw_tile.cu: A^T operand built in tensor memory, G tile staged once
+    per tile, fixed-order reduction) on levels where the tiled forward kernel runs.  Default OFF: the deterministic
+    option -- measured 1.3x (level 0, 32x32) to 2.1-3.5x (levels 1-2) slower than the pair-list kernel
+    (profiles/r2f_time_dw_tile.txt): TMEM capacity forces 4-12 CTAs to re-stage every tile (one 32-channel block and a
+    subset of the offsets each) and the loaders' two dependent global round trips per tile bound it."""
     _dw_tiled[0] = bool(on)
 
 

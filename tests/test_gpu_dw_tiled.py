@@ -39,7 +39,7 @@ def test_tiled_dw_matches_pair_kernel_and_is_reproducible(levels, level, ca, cg)
         assert dw is not None, "shape not taken by the tiled weight gradient"
         assert dw.shape == ref.shape == (27, ca, cg)
         err = float((dw - ref).norm() / ref.norm())
-        assert err < 3e-5, err   # measured <= 1.5e-5 (fp32 sums in different orders)
+        assert err < 6e-5, err   # measured <= 3.6e-5 (fp32 sums in different orders: 128-row tiles vs 4096-pair chunks)
         # against exact fp64 on one offset (k = 4) and the centre (k = 13)
         nbr = lvl.subm_map().long()
         for k in (4, 13, 26):
