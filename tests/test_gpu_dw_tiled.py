@@ -71,3 +71,44 @@ def test_tiled_dw_overflow_slots(levels):
         ops.set_halo_capacity(old)
         lvl.plan = None
         scn.set_precision("fp32")
+
+
+@pytest.mark.parametrize("level,ca,cg", [(0, 32, 32), (1, 64, 64), (3, 128, 128), (2, 40, 16)])
+def test_blocked_pair_table_and_kernel_variants(levels, level, ca, cg):
+    """b200scn_pair_lists_blocked: same lists as b200scn_pair_lists_ordered + a row-block table whose segments partition
+    every offset's list at the Morton-block boundaries; b200scn_pair_dw_blocked and the 64-pairs-per-stage variant of
+    b200scn_pair_dw agree with the default kernel (fp32 sums in another order)."""
+    import sparseconvnet as scn
+    from sparseconvnet import ops
+    from sparseconvnet.metadata import build_pairs, pair_row_block
+    lvl = levels[level]
+    scn.set_precision("tf32")
+    try:
+        perm = lvl.tile_plan(ops._halo["hcap"]).perm
+        total = sum(lvl.rule_counts())
+        pin, pout, offs = build_pairs(lvl.subm_map(), lvl.n, 27, total, order=perm)
+        rb = pair_row_block(lvl.n, 27)
+        bin_, bout, boffs, (blk, nblk) = build_pairs(lvl.subm_map(), lvl.n, 27, total, order=perm, row_block=rb)
+        assert torch.equal(bin_[:total], pin[:total]) and torch.equal(bout[:total], pout[:total]) and torch.equal(boffs, offs)
+        blk_h, offs_h = blk.cpu().long(), offs.cpu().long()
+        assert nblk == (lvl.n + rb - 1) // rb and blk_h.numel() == 27 * nblk + 1
+        assert bool((blk_h[1:] >= blk_h[:-1]).all()) and int(blk_h[-1]) == total
+        assert torch.equal(blk_h[0:27 * nblk:nblk], offs_h[:27])          # block 0 of offset k starts where list k starts
+        # every pair of segment (k, b) has its row inside Morton block b
+        rank = torch.empty(lvl.n, dtype=torch.long, device="cuda")
+        rank[perm.long()] = torch.arange(lvl.n, device="cuda")
+        seg = torch.bucketize(torch.arange(total), blk_h[1:], right=True)   # flat segment index of every pair
+        assert torch.equal((rank[pout[:total].long()].cpu() // rb), seg % nblk)
+        torch.manual_seed(7)
+        a = to_tf32(torch.randn(lvl.n, ca, device="cuda"))
+        g = to_tf32(torch.randn(lvl.n, cg, device="cuda"))
+        ref = ops.pair_dw(a, g, pin, pout, offs, 27, lvl.n)
+        got = ops.pair_dw_blocked(a, g, pin, pout, blk, nblk, 27)
+        assert got is not None and float((got - ref).norm() / ref.norm()) < 3e-5
+        scn.set_option("dw_pairs", 64)
+        got64 = ops.pair_dw(a, g, pin, pout, offs, 27, lvl.n)
+        scn.set_option("dw_pairs", 32)
+        assert float((got64 - ref).norm() / ref.norm()) < 3e-5
+    finally:
+        scn.set_option("dw_pairs", 32)
+        scn.set_precision("fp32")
