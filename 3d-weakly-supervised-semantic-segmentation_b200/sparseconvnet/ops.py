@@ -306,6 +306,23 @@ def subm_dw_tiled(a, g, level):
     return dw
 
 
+# Experiment switch (B200SCN_DW_SIDE=1 / set_dw_side_stream): the weight gradient of a submanifold layer on a second stream,
+# concurrent with the layer's input gradient (they are independent); both streams are joined before backward returns.
+_dw_side = [os.environ.get("B200SCN_DW_SIDE", "0") == "1"]
+_side_streams = {}
+
+
+def set_dw_side_stream(on):
+    _dw_side[0] = bool(on)
+
+
+def _side_stream(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _side_streams:
+        _side_streams[idx] = torch.cuda.Stream(device=idx)
+    return _side_streams[idx]
+
+
 class SubmanifoldConvFn(torch.autograd.Function):
     """scn.SubmanifoldConvolution (models/SparseConvNet.py:62,117,119): replaces upstream
     SubmanifoldConvolution_updateOutput / _backward."""
@@ -322,11 +339,23 @@ class SubmanifoldConvFn(torch.autograd.Function):
         x, w = ctx.saved_tensors
         level = ctx.level
         dx = dw = None
+        tiled = _precision[0] == 1 and _use_tiled(level.n)
+        if (_dw_side[0] and tiled and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and not _dw_tiled[0]
+                and not _dw_blocked[0] and _prof is None):
+            # rulebook first, on the main stream (it is cached on the level and used by later layers on either stream)
+            pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
+            main, side = torch.cuda.current_stream(g.device), _side_stream(g.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dw = pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level)
+            dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True, prepared=ctx.w_bwd))
+            main.wait_stream(side)
+            dw.record_stream(main)
+            return dx, dw, None, (g if ctx.needs_input_grad[3] else None), None
         if ctx.needs_input_grad[0]:
             # pair (in=i, out=o) at offset k <=> o = nbr[i][26-k]:  dx[i] = sum_k' g[nbr[i][k']] @ w[26-k']^T
             dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True, prepared=ctx.w_bwd))
         if ctx.needs_input_grad[1]:
-            tiled = _precision[0] == 1 and _use_tiled(level.n)
             if tiled and _dw_tiled[0]:
                 dw = subm_dw_tiled(x, g, level)
             if dw is None and tiled and _dw_blocked[0]:
