@@ -373,6 +373,14 @@ def run_b200(args):
             dist.all_gather(allr, mine)
             extra["per_rank"] = [{"ms_per_step": float(a[0]), "comm_exposed_ms": float(a[1]), "voxels_per_step": float(a[2])}
                                  for a in allr]
+            # outside the timed region: after the last step's all-reduce every rank must hold BIT-IDENTICAL gradients
+            # (a wrapping int64 sum over the bit patterns of the flat gradient buffer is compared across ranks)
+            if not eval_reps:
+                h = flat.flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+                hs = [torch.zeros_like(h) for _ in range(world)]
+                dist.all_gather(hs, h)
+                extra["grads_identical_across_ranks"] = all(int(x) == int(hs[0]) for x in hs)
+                assert extra["grads_identical_across_ranks"], "ranks hold different gradients after the all-reduce"
             ms, vox = float(tmax[0]), float(t[1])
         else:
             vox = float(t[1])
@@ -469,6 +477,7 @@ def run_b200(args):
         if world > 1:
             line["comm_exposed_ms"] = ex["comm_exposed_ms"]
             line["per_rank"] = ex.get("per_rank")
+            line["grads_identical_across_ranks"] = ex.get("grads_identical_across_ranks")
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample(args.config, args.points)
         print(json.dumps(line), flush=True)

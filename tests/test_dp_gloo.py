@@ -76,3 +76,48 @@ def test_flat_gradient_allreduce_world2():
     assert out[0][0] and out[1][0]
     assert out[0][1] and out[1][1]
     assert sorted(out[0][2] + out[1][2]) == [0, 1, 2, 3, 4]
+
+
+def _worker_net(rank, world, port, out):
+    """A real encoder (the CPU oracle's SparseConvUNet, one scene per rank): after the exchange every rank holds the mean of
+    the per-shard single-process gradients, bit-identical across ranks."""
+    sys.path.insert(0, PKG)
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from b200scn_dp import FlatGrads, shard_scenes
+    from b200scn_synth import build_encoder, make_batch
+    from oracle import scn_oracle as ref
+    torch.manual_seed(0)                       # identical initial weights on every rank
+    net = build_encoder(ref, "SparseConvUNet", 4, 1, True)
+    flat = FlatGrads(net.parameters(), bucket_bytes=4096)
+    scenes = shard_scenes(world, rank, world)  # one scene each
+    coords, feats, _ = make_batch(scenes, 8, n_points=1500)
+    flat.zero()
+    net([coords, feats]).pow(2).mean().backward()
+    local = torch.cat([p.grad.reshape(-1).clone() for p in net.parameters()])   # this shard's single-process gradient
+    flat.allreduce_mean()
+    now = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean = sum(gathered) / world
+    rel = float((now - mean).norm() / mean.norm())
+    everyone = [torch.zeros_like(now) for _ in range(world)]
+    dist.all_gather(everyone, now)
+    out[rank] = (rel, all(torch.equal(everyone[0], e) for e in everyone), len(flat.buckets))
+    dist.destroy_process_group()
+
+
+def test_encoder_gradients_are_the_mean_of_the_shards():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_net, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        rel, identical, nb = out[r]
+        assert rel < 1e-6, rel          # = the mean of the per-shard gradients (bar: 1e-5)
+        assert identical                 # bit-identical on every rank
+        assert nb > 3                    # several buckets, launched from hooks during backward
