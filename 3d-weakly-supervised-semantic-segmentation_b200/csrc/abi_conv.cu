@@ -186,6 +186,40 @@ extern "C" int b200scn_prep_weight_tf32_both(const float *w0, int K, int a, int 
   return 0;
 }
 
+// Every layer of a network in ONE launch: items[i] = {w0, out_fwd, out_bwd, K, a, b, flip_bwd, first element} (device table,
+// ascending first element); element e of the concatenation is located by a binary search over the table.
+namespace b200scn {
+__global__ void prep_weight_batch_kernel(const b200scn_prep_item *__restrict__ items, int n_items, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&items[mid].first) <= e) lo = mid; else hi = mid - 1;
+    }
+    const b200scn_prep_item it = items[lo];
+    const int64_t le = e - it.first, ab = (int64_t)it.a * it.b;
+    const int k = (int)(le / ab);
+    const int r = (int)(le - (int64_t)k * ab);
+    uint32_t t;
+    const int kk = it.flip_bwd ? it.K - 1 - k : k;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__ldg(it.w0 + (int64_t)kk * ab + r)));
+    it.out_bwd[le] = __uint_as_float(t);
+    const int co = r / it.a, ci = r - co * it.a;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(__ldg(it.w0 + ((int64_t)k * it.a + ci) * it.b + co)));
+    it.out_fwd[le] = __uint_as_float(t);
+  }
+}
+}  // namespace b200scn
+
+extern "C" int b200scn_prep_weight_tf32_batch(const b200scn_prep_item *items_dev, int n_items, int64_t total, void *stream) {
+  if (n_items <= 0 || total <= 0) return 0;
+  const unsigned blocks = (unsigned)min((int64_t)kNumSMs * 16, ceil_div(total, 256));
+  prep_weight_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(items_dev, n_items, total);
+  SCN_CHECK_LAUNCH("prep_weight_tf32_batch");
+  count_launch(1);
+  return 0;
+}
+
 extern "C" int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transposed, int flip, float *out,
                                         void *stream) {
   const int64_t n = (int64_t)K * a * b;

@@ -49,6 +49,7 @@ SIGNATURES = {
     "b200scn_subm_dw_tiled": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _sz, _vp]),
     "b200scn_prep_weight_tf32": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b200scn_prep_weight_tf32_both": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "b200scn_prep_weight_tf32_batch": (_i32, [_vp, _i32, _i64, _vp]),
     "b200scn_scatter_conv": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _i32, _vp]),
     "b200scn_group_tiles": (_i32, [_vp, _i32, _i64, _vp, _vp]),
     "b200scn_grouped_conv": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _i32, _i32, _vp, _i64, _vp]),

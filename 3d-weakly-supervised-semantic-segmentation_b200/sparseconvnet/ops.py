@@ -4,6 +4,7 @@ Each function cites the upstream scn entry point it replaces and the
 reaches it.  All tensors are CUDA fp32; there is no CPU path.
 """
 import os
+import weakref
 
 import torch
 
@@ -124,16 +125,116 @@ class GemmWeight:
         return out
 
 
+class _WeightCache:
+    """Prepared (K-major, TF32-rounded) operands of every convolution weight, refreshed ONCE per optimiser step.
+
+    Each layer keeps two persistent buffers (forward / backward-input operand).  A layer whose parameter has not changed
+    since they were written (same storage, same autograd version counter) reuses them without a launch; the first layer
+    that finds its parameter changed -- the first convolution after optimizer.step() -- refreshes EVERY registered layer
+    in one `b200scn_prep_weight_tf32_batch` launch (cfg3: 1 launch instead of 73 per step).  In-place updates through
+    autograd-visible ops (optimisers, load_state_dict, copy_) bump the version counter; edits through `.data` do not: call
+    `invalidate_weight_cache()` after those.  B200SCN_WEIGHT_CACHE=0 restores one preparation launch per layer and call."""
+
+    def __init__(self):
+        self.entries = {}       # (device, data_ptr, K, a, b, flip) -> entry
+        self.tables = {}        # device index -> (device table tensor, n_items, total elements, list of entries) or None
+
+    def invalidate(self):
+        for e in self.entries.values():
+            e["version"] = -1
+
+    def clear(self):
+        self.entries.clear()
+        self.tables.clear()
+
+    def get(self, w, flip_bwd):
+        K, a, b = w.shape
+        dev = w.device.index if w.device.index is not None else torch.cuda.current_device()
+        key = (dev, w.data_ptr(), K, a, b, bool(flip_bwd))
+        e = self.entries.get(key)
+        if e is not None and e["ref"]() is None:      # the parameter died and its address was reused
+            del self.entries[key]
+            self.tables.pop(dev, None)
+            e = None
+        if e is None:
+            if len(self.entries) > 4096:                # (a process that keeps building new models)
+                self.clear()
+            e = {"ref": weakref.ref(w._base if w._base is not None else w), "ptr": w.data_ptr(), "shape": (K, a, b),
+                 "flip": bool(flip_bwd), "dev": dev, "version": -1,
+                 "fwd": torch.empty((K, b, a), dtype=torch.float32, device=w.device),
+                 "bwd": torch.empty((K, a, b), dtype=torch.float32, device=w.device)}
+            self.entries[key] = e
+            self.tables.pop(dev, None)
+            self._prep_one(w, e)
+            return e["fwd"], e["bwd"]
+        if e["version"] != w._version:
+            self._refresh(dev, w)
+        return e["fwd"], e["bwd"]
+
+    @staticmethod
+    def _alive(e):
+        t = e["ref"]()
+        if t is None or not t.is_cuda:
+            return False
+        st = t.untyped_storage()
+        n = e["shape"][0] * e["shape"][1] * e["shape"][2] * 4
+        return st.data_ptr() <= e["ptr"] and e["ptr"] + n <= st.data_ptr() + st.nbytes()
+
+    def _prep_one(self, w, e):
+        K, a, b = e["shape"]
+        check(lib.b200scn_prep_weight_tf32_both(ptr(w), K, a, b, 1 if e["flip"] else 0, ptr(e["fwd"]), ptr(e["bwd"]),
+                                                _lib.stream_for(w)))
+        e["version"] = w._version
+
+    def _refresh(self, dev, w):
+        tab = self.tables.get(dev)
+        if tab is None:
+            live = [e for e in self.entries.values() if e["dev"] == dev and self._alive(e)]
+            for k in [k for k, e in self.entries.items() if e["dev"] == dev and not self._alive(e)]:
+                del self.entries[k]          # the parameter moved (model.cpu() / .cuda()) or died: its old address is not read again
+            rows, first = [], 0
+            for e in live:
+                K, a, b = e["shape"]
+                rows.append([e["ptr"], e["fwd"].data_ptr(), e["bwd"].data_ptr(), K | (a << 32), b | (int(e["flip"]) << 32), first])
+                first += K * a * b
+            tab = (torch.tensor(rows, dtype=torch.int64, device=w.device), len(live), first, live)
+            self.tables[dev] = tab
+        table, n, total, live = tab
+        check(lib.b200scn_prep_weight_tf32_batch(ptr(table), n, total, _lib.stream_for(w)))
+        for e in live:
+            t = e["ref"]()
+            if t is not None:
+                e["version"] = t._version
+
+
+_weight_cache = _WeightCache()
+_weight_cache_on = [os.environ.get("B200SCN_WEIGHT_CACHE", "1") != "0"]
+
+
+def invalidate_weight_cache():
+    """Force every convolution weight to be prepared again (needed only after editing parameters through `.data`)."""
+    _weight_cache.invalidate()
+
+
+def set_weight_cache(on):
+    _weight_cache_on[0] = bool(on)
+    _weight_cache.clear()
+
+
 def prep_both(w, flip_bwd):
-    """K-major TF32 operands of BOTH directions of one layer in one launch: (forward: w[k], backward-input: w[k]^T with the
-    offsets mirrored if flip_bwd).  The forward pass makes them together and hands the second to its backward, so a
-    training step prepares each layer's weights once instead of twice.  None when the tensor-core path is off."""
+    """K-major TF32 operands of BOTH directions of one layer (forward: w[k], backward-input: w[k]^T with the offsets
+    mirrored if flip_bwd).  The forward pass gets them together and hands the second to its backward; with the weight cache
+    (default) they are persistent buffers refreshed once per optimiser step for all layers in one launch, otherwise one
+    launch per layer and call.  None when the tensor-core path is off."""
     if _precision[0] != 1:
         return None, None
+    cacheable = _weight_cache_on[0] and w.is_contiguous() and w.data_ptr() % 16 == 0   # (a non-contiguous view is a new copy per call)
     w = w.contiguous()
     K, a, b = w.shape
     if lib.b200scn_gather_conv_tf32_ok(a, b, a) != 1 or lib.b200scn_gather_conv_tf32_ok(b, a, b) != 1:
         return None, None
+    if cacheable:
+        return _weight_cache.get(w, flip_bwd)
     fwd = torch.empty((K, b, a), dtype=torch.float32, device=w.device)
     bwd = torch.empty((K, a, b), dtype=torch.float32, device=w.device)
     check(lib.b200scn_prep_weight_tf32_both(ptr(w), K, a, b, 1 if flip_bwd else 0, ptr(fwd), ptr(bwd), _lib.stream_for(w)))
@@ -331,7 +432,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
     def forward(ctx, x, w, level, addend=None, x_rounded=False):
         ctx.level = level
         ctx.save_for_backward(x, w)
-        fwd, ctx.w_bwd = prep_both(w, True) if ctx.needs_input_grad[0] else (None, None)
+        fwd, ctx.w_bwd = prep_both(w, True) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return subm_conv(x, level, GemmWeight(w, prepared=fwd), addend=addend, round_a=not x_rounded)
 
     @staticmethod
@@ -377,7 +478,7 @@ class ConvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        fwd, ctx.w_bwd = prep_both(w, False) if ctx.needs_input_grad[0] else (None, None)
+        fwd, ctx.w_bwd = prep_both(w, False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return gather_conv(x, down.child_map(), down.coarse.n, down.K, GemmWeight(w, prepared=fwd), rules=down.fine.n)
 
     @staticmethod
@@ -401,7 +502,7 @@ class DeconvolutionFn(torch.autograd.Function):
     def forward(ctx, x, w, down):
         ctx.down = down
         ctx.save_for_backward(x, w)
-        fwd, ctx.w_bwd = prep_both(w, False) if ctx.needs_input_grad[0] else (None, None)
+        fwd, ctx.w_bwd = prep_both(w, False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w, prepared=fwd), down)
 
     @staticmethod
@@ -452,7 +553,7 @@ class NetworkInNetworkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
         ctx.save_for_backward(x, w)
-        fwd, ctx.w_bwd = prep_both(w.unsqueeze(0), False) if ctx.needs_input_grad[0] else (None, None)
+        fwd, ctx.w_bwd = prep_both(w.unsqueeze(0), False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return gather_conv(x, None, x.shape[0], 1, GemmWeight(w.unsqueeze(0), prepared=fwd))
 
     @staticmethod

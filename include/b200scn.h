@@ -150,6 +150,16 @@ int b200scn_prep_weight_tf32(const float *w0, int K, int a, int b, int transpose
  * operand of "multiply by w0[k]^T" with the offsets mirrored if flip_bwd (backward-input; flip for submanifold 3^3) */
 int b200scn_prep_weight_tf32_both(const float *w0, int K, int a, int b, int flip_bwd, float *out_fwd, float *out_bwd,
                                   void *stream);
+/* The same for MANY layers in one launch (a training step prepares every layer's operands once, after the optimiser has
+ * changed the weights): a device-resident table, ascending `first` = index of the item's first element in the
+ * concatenation of all items (K*a*b elements each); total = sum of all K*a*b. */
+typedef struct b200scn_prep_item {
+  const float *w0;
+  float *out_fwd, *out_bwd;
+  int32_t K, a, b, flip_bwd;
+  int64_t first;
+} b200scn_prep_item;
+int b200scn_prep_weight_tf32_batch(const b200scn_prep_item *items_dev, int n_items, int64_t total, void *stream);
 
 /* Offset-sorted ("grouped") strided convolution on the tensor cores, for the directions in which every output row has
  * exactly one rule (Deconvolution_updateOutput, backward-input of Convolution): the scn-form rulebook
