@@ -100,39 +100,63 @@ def _bn_feeds_conv(m, nxt):
                                                                    NetworkInNetwork))
 
 
+def _fusable_join(m, nxt):
+    """ConcatTable(Identity, Sequential(BatchNorm, ...)) + JoinTable -- the down/up path of scn.UNet
+    (models/SparseConvNet.py:126-140): x feeds the BatchNorm AND the joined output."""
+    if not (_fuse_residual[0] and type(m) is ConcatTable and type(nxt) is JoinTable and len(m._modules) == 2):
+        return False
+    branch = m._modules["1"]
+    if type(m._modules["0"]) is not Identity or type(branch) is not Sequential or len(branch._modules) < 2:
+        return False
+    return isinstance(list(branch._modules.values())[0], BatchNormalization)
+
+
+def _run_modules(mods, input):
+    """Sequential.forward over a list of modules, with the fusion peepholes (module tree and results unchanged)."""
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if i + 1 < len(mods) and _fusable_residual(m, mods[i + 1]):
+            branch = list(m._modules["1"]._modules.values())
+            y = input
+            if isinstance(branch[0], BatchNormalization) and len(branch) > 1 and input.features.requires_grad:
+                # x feeds the BatchNorm AND the skip: one function returns both, so that backward sums the two
+                # gradients inside the BatchNorm backward kernel
+                y = branch[0](input, feeds_conv=_bn_feeds_conv(branch[0], branch[1]), want_alias=True)   # (hooks fire)
+                input = y.skip_alias
+                rest = list(enumerate(branch[:-1]))[1:]
+            else:
+                rest = list(enumerate(branch[:-1]))
+            skip = m._modules["0"](input)
+            for j, mod in rest:
+                y = mod(y, feeds_conv=True) if _bn_feeds_conv(mod, branch[j + 1]) else mod(y)
+            input = branch[-1](y, addend=skip.features)
+            i += 2
+            continue
+        if i + 1 < len(mods) and _fusable_join(m, mods[i + 1]) and input.features.requires_grad:
+            # same for the U-Net's down/up path: the gradient that comes back through the joined copy of x is summed inside
+            # the BatchNorm backward kernel instead of by an autograd add over the whole tensor (6 per step in the m=32 UNet)
+            branch = list(m._modules["1"]._modules.values())
+            y = branch[0](input, feeds_conv=_bn_feeds_conv(branch[0], branch[1]), want_alias=True)
+            deep = _run_modules(branch[1:], y)
+            input = mods[i + 1]([m._modules["0"](y.skip_alias), deep])
+            i += 2
+            continue
+        if i + 1 < len(mods) and _bn_feeds_conv(m, mods[i + 1]):
+            input = m(input, feeds_conv=True)
+        else:
+            input = m(input)
+        i += 1
+    return input
+
+
 class Sequential(torch.nn.Sequential):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
         return self
 
     def forward(self, input):
-        mods = list(self._modules.values())
-        i = 0
-        while i < len(mods):
-            m = mods[i]
-            if i + 1 < len(mods) and _fusable_residual(m, mods[i + 1]):
-                branch = list(m._modules["1"]._modules.values())
-                y = input
-                if isinstance(branch[0], BatchNormalization) and len(branch) > 1 and input.features.requires_grad:
-                    # x feeds the BatchNorm AND the skip: one function returns both, so that backward sums the two
-                    # gradients inside the BatchNorm backward kernel
-                    y = branch[0](input, feeds_conv=_bn_feeds_conv(branch[0], branch[1]), want_alias=True)   # (hooks fire)
-                    input = y.skip_alias
-                    rest = list(enumerate(branch[:-1]))[1:]
-                else:
-                    rest = list(enumerate(branch[:-1]))
-                skip = m._modules["0"](input)
-                for j, mod in rest:
-                    y = mod(y, feeds_conv=True) if _bn_feeds_conv(mod, branch[j + 1]) else mod(y)
-                input = branch[-1](y, addend=skip.features)
-                i += 2
-                continue
-            if i + 1 < len(mods) and _bn_feeds_conv(m, mods[i + 1]):
-                input = m(input, feeds_conv=True)
-            else:
-                input = m(input)
-            i += 1
-        return input
+        return _run_modules(list(self._modules.values()), input)
 
     def input_spatial_size(self, out_size):
         for m in reversed(self._modules.values()):
