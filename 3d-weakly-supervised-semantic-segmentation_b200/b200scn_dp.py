@@ -92,6 +92,27 @@ class FlatGrads:
 
     def _launch(self, b):
         lo, hi, f0, f1 = self.buckets[b]
+        side = self._deferred_stream()
+        if side is not None:
+            # deferred weight gradients (sparseconvnet.ops.set_deferred_dw): some gradients of the bucket are still being
+            # computed on the second stream, the others on the main stream -- pack and launch from the second stream once it
+            # has caught up with the main stream's position, so that the main stream never waits for a weight gradient
+            side.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(side):
+                self._pack_and_reduce(lo, hi, f0, f1)
+        else:
+            self._pack_and_reduce(lo, hi, f0, f1)
+
+    def _deferred_stream(self):
+        if not self.flat.is_cuda:
+            return None
+        try:
+            from sparseconvnet import ops
+        except Exception:
+            return None
+        return ops._side_stream(self.flat.device) if ops._dw_defer[0] else None
+
+    def _pack_and_reduce(self, lo, hi, f0, f1):
         grads = [self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i])
                  for i in range(lo, hi)]
         torch._foreach_copy_(self.views[lo:hi], grads)

@@ -14,7 +14,7 @@ from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNor
                       SparseConvNetTensor, SubmanifoldConvolution, UnPooling)
 from .networks import FullyConvolutionalNet, UNet
 from .modules import MaxPooling, SceneMeanPooling, SparseToDense, set_fusion  # noqa: F401
-from .ops import get_precision, invalidate_weight_cache, set_precision, set_tiled, set_weight_cache
+from .ops import get_precision, invalidate_weight_cache, set_deferred_dw, set_precision, set_tiled, set_weight_cache
 from .utils import checkpoint_restore, checkpoint_save, is_power2
 
 forward_pass_hidden_states = 0

@@ -3,6 +3,7 @@
 Each function cites the upstream scn entry point it replaces and the reference call site that
 reaches it.  All tensors are CUDA fp32; there is no CPU path.
 """
+import collections
 import os
 import weakref
 
@@ -417,6 +418,83 @@ def set_dw_side_stream(on):
     _dw_side[0] = bool(on)
 
 
+# Deferred weight gradients (set_deferred_dw, opt-in): every submanifold layer's weight gradient is queued on the second
+# stream and NOT waited for by the layer; the streams are joined once, by an autograd-engine callback at the end of the
+# backward pass; the gradients are stored into `.grad` directly (they bypass AccumulateGrad, whose copy would otherwise read
+# them on the main stream too early) and the parameters' post-accumulate hooks are run by hand.  The weight gradients leave the critical path: they fill the SMs that the small
+# levels of the U-Net (1.5 % of the voxels, ~2.5 ms of nearly idle GPU per backward) and the tails of the big kernels leave
+# empty.  Contract: loss.backward() still returns with every .grad complete; torch.autograd.grad() and hooks on the
+# weight gradients (other than post-accumulate hooks) are not supported in this mode.
+_dw_defer = [False]
+_deferred = {"queued": False, "device": None, "held": collections.deque()}
+
+
+def set_deferred_dw(on):
+    _dw_defer[0] = bool(on)
+
+
+def _finish_deferred():
+    """End of the backward pass (autograd-engine callback): the main stream waits for the deferred weight gradients."""
+    dev = _deferred["device"]
+    _deferred["queued"] = False
+    if dev is not None:
+        torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+    _deferred["held"].clear()      # (their memory is protected by record_stream until the second stream is done with it)
+
+
+def _deliver_deferred(param, dw, side):
+    """Store a deferred weight gradient (still being computed on `side`) into param.grad.  Autograd still runs the
+    parameter's post-accumulate hooks when its AccumulateGrad node is reached with the (undefined) gradient this layer
+    returns -- the data-parallel bucket hooks of b200scn_dp.FlatGrads, which in this mode pack and launch their collectives
+    on `side` too, so nothing on the main stream ever waits for a weight gradient before the end of backward."""
+    dw = dw.view_as(param)
+    with torch.no_grad():
+        if param.grad is None:
+            param.grad = dw
+        else:
+            with torch.cuda.stream(side):
+                param.grad.add_(dw)
+
+
+def _param_of(w):
+    """The Parameter behind a weight view (the layers pass `weight.view(...)` / `weight.unsqueeze(0)`), or None."""
+    b = w._base if w._base is not None else w
+    return b if isinstance(b, torch.nn.Parameter) and b.numel() == w.numel() else None
+
+
+def _defer_ok(param):
+    return (_dw_defer[0] and _precision[0] == 1 and param is not None and not _dw_tiled[0] and not _dw_blocked[0]
+            and _prof is None)
+
+
+def _run_deferred(param, inputs, fn):
+    """Queue fn() -> dW on the second stream after everything the main stream has enqueued so far, and deliver it."""
+    dev = inputs[0].device
+    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        dw = fn()
+    # the inputs belong to the main stream's allocator: it must not hand their memory out again before the second stream
+    # has read them; dw is read by the main stream (optimiser) after the join
+    for t in inputs:
+        t.record_stream(side)
+    dw.record_stream(main)
+    # keep the inputs referenced until the second stream has consumed them: the autograd engine accumulates IN PLACE into
+    # gradient buffers it solely owns (a layer may hand its incoming gradient on as the gradient of its addend), which
+    # would change `g` under the queued kernel; a second reference makes it allocate instead
+    ev = torch.cuda.Event()
+    ev.record(side)
+    held = _deferred["held"]
+    held.append((ev, inputs))
+    while held and held[0][0].query():
+        held.popleft()
+    _deferred["device"] = dev
+    if not _deferred["queued"]:
+        _deferred["queued"] = True
+        torch.autograd.Variable._execution_engine.queue_callback(_finish_deferred)
+    _deliver_deferred(param, dw, side)
+
+
 def _side_stream(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _side_streams:
@@ -431,6 +509,7 @@ class SubmanifoldConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, level, addend=None, x_rounded=False):
         ctx.level = level
+        ctx.param = _param_of(w)                        # (deferred-dW mode delivers the weight gradient to it directly)
         ctx.save_for_backward(x, w)
         fwd, ctx.w_bwd = prep_both(w, True) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return subm_conv(x, level, GemmWeight(w, prepared=fwd), addend=addend, round_a=not x_rounded)
@@ -441,6 +520,16 @@ class SubmanifoldConvFn(torch.autograd.Function):
         level = ctx.level
         dx = dw = None
         tiled = _precision[0] == 1 and _use_tiled(level.n)
+        base = ctx.param
+        if ctx.needs_input_grad[1] and _defer_ok(base):
+            if tiled:
+                pin, pout, offs = level.subm_pairs_ordered(level.tile_plan(_halo["hcap"]).perm)
+            else:
+                pin, pout, offs = level.subm_pairs()
+            _run_deferred(base, (x, g), lambda: pair_dw(x, g, pin, pout, offs, 27, level.n, rules=level))
+            if ctx.needs_input_grad[0]:
+                dx = subm_conv(g, level, GemmWeight(w, transposed=True, flip=True, prepared=ctx.w_bwd))
+            return dx, None, None, (g if ctx.needs_input_grad[3] else None), None
         if (_dw_side[0] and tiled and ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and not _dw_tiled[0]
                 and not _dw_blocked[0] and _prof is None):
             # rulebook first, on the main stream (it is cached on the level and used by later layers on either stream)
@@ -477,6 +566,7 @@ class ConvolutionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, down):
         ctx.down = down
+        ctx.param = _param_of(w)
         ctx.save_for_backward(x, w)
         fwd, ctx.w_bwd = prep_both(w, False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return gather_conv(x, down.child_map(), down.coarse.n, down.K, GemmWeight(w, prepared=fwd), rules=down.fine.n)
@@ -490,7 +580,10 @@ class ConvolutionFn(torch.autograd.Function):
             dx = scatter_conv(g, down.child_map(), down.fine.n, down.K, GemmWeight(w, transposed=True, prepared=ctx.w_bwd), down)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
-            dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
+            if _defer_ok(ctx.param):
+                _run_deferred(ctx.param, (x, g), lambda: pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n))
+            else:
+                dw = pair_dw(x, g, pin, pout, offs, down.K, down.coarse.n, rules=down.fine.n)
         return dx, dw, None
 
 
@@ -501,6 +594,7 @@ class DeconvolutionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, down):
         ctx.down = down
+        ctx.param = _param_of(w)
         ctx.save_for_backward(x, w)
         fwd, ctx.w_bwd = prep_both(w, False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return scatter_conv(x, down.child_map(), down.fine.n, down.K, GemmWeight(w, prepared=fwd), down)
@@ -515,7 +609,10 @@ class DeconvolutionFn(torch.autograd.Function):
                              rules=down.fine.n)
         if ctx.needs_input_grad[1]:
             pin, pout, offs = down.child_pairs()
-            dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n)
+            if _defer_ok(ctx.param):
+                _run_deferred(ctx.param, (x, g), lambda: pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n))
+            else:
+                dw = pair_dw(x, g, pout, pin, offs, down.K, down.coarse.n, rules=down.fine.n)
         return dx, dw, None
 
 
@@ -552,6 +649,7 @@ class NetworkInNetworkFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w):
+        ctx.param = w if isinstance(w, torch.nn.Parameter) else _param_of(w)
         ctx.save_for_backward(x, w)
         fwd, ctx.w_bwd = prep_both(w.unsqueeze(0), False) if (ctx.needs_input_grad[0] or _weight_cache_on[0]) else (None, None)
         return gather_conv(x, None, x.shape[0], 1, GemmWeight(w.unsqueeze(0), prepared=fwd))
@@ -563,7 +661,10 @@ class NetworkInNetworkFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gather_conv(g, None, g.shape[0], 1, GemmWeight(w.unsqueeze(0), transposed=True, prepared=ctx.w_bwd))
         if ctx.needs_input_grad[1]:
-            dw = pair_dw(x, g, None, None, None, 1, x.shape[0])[0]
+            if _defer_ok(ctx.param):
+                _run_deferred(ctx.param, (x, g), lambda: pair_dw(x, g, None, None, None, 1, x.shape[0])[0])
+            else:
+                dw = pair_dw(x, g, None, None, None, 1, x.shape[0])[0]
         return dx, dw
 
 
