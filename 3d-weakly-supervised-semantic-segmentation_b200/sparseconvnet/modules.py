@@ -219,6 +219,7 @@ class InputLayer(Module):
 
     def forward(self, input):
         coords, feats = input[0], input[1]
+        ops.recover_deferred()   # (a backward pass that died half-way in deferred-dW mode leaves the streams unjoined)
         if self.mode not in (1, 2, 3, 4):
             raise NotImplementedError("InputLayer mode %r (supported: 1 last, 2 first, 3 sum, 4 mean)" % (self.mode,))
         if not feats.is_cuda:

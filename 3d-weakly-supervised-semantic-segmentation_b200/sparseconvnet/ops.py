@@ -442,6 +442,13 @@ def _finish_deferred():
     _deferred["held"].clear()      # (their memory is protected by record_stream until the second stream is done with it)
 
 
+def recover_deferred():
+    """Called at the start of every forward pass: if the previous backward pass raised before the engine ran its end-of-pass
+    callback, join the streams now and forget the stale state (no-op otherwise)."""
+    if _deferred["queued"]:
+        _finish_deferred()
+
+
 def _deliver_deferred(param, dw, side):
     """Store a deferred weight gradient (still being computed on `side`) into param.grad.  Autograd still runs the
     parameter's post-accumulate hooks when its AccumulateGrad node is reached with the (undefined) gradient this layer
