@@ -517,10 +517,16 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("B200SCN_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # A hang (a collective some rank never reaches, a kernel that never ends) must not sit until the caller's time limit: after
+    # B200SCN_BENCH_WATCHDOG_S seconds (default 600: a normal run takes 1-3 minutes at any N) every thread's Python stack is
+    # written to stderr and the process exits, which makes torch.distributed.run stop the other ranks.
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("B200SCN_BENCH_WATCHDOG_S", "600")), exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    faulthandler.cancel_dump_traceback_later()
 
 
 if __name__ == "__main__":
