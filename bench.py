@@ -484,7 +484,7 @@ def run_b200(args):
             "config": {"workload": args.config, "encoder": "%s m=%d block_reps=%d residual=%s" % (kind, m, reps, res),
                        "scale": scale, "batch_per_gpu": batch, "points_per_scene": args.points,
                        "voxels_per_step_per_gpu": vox / args.steps / world, "parallelism": "dp%d" % world,
-                       "step": step_desc,
+                       "step": step_desc, "deferred_dw": bool(defer_dw),
                        "l2": "inputs larger than L2: >1 GB of activations per step, fresh coordinates each step"},
             "clocks": clocks,
             "e2e": {"value": vox_e / (ms_e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e / args.steps,
