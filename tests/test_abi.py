@@ -53,3 +53,10 @@ def test_no_cpu_fallback_and_loud_failure():
         scn.InputLayer(3, 4096, mode=4)([coords, torch.zeros(4, 3)])   # CPU features are refused, not emulated
     src = open(os.path.join(ROOT, "3d-weakly-supervised-semantic-segmentation_b200", "sparseconvnet", "ops.py")).read()
     assert "oracle" not in src   # the product never routes through the test oracle
+
+
+def test_integration_doc_names_every_entry():
+    """INTEGRATION.md maps each C entry to the reference interface it replaces (or says what it is for)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing
